@@ -1,0 +1,125 @@
+/*
+ * gbd_pcg.h -- flat C ABI of the B200-native GBD-PCG solver (libgbdpcg.so).
+ *
+ * This is the drop-in boundary for the one hot path of A2R-Lab/MPCGPU: the block-tridiagonal
+ * preconditioned-conjugate-gradient solve of  S * lambda = gamma  with preconditioner Pinv.
+ * Each entry point names the reference interface it replaces (paths relative to the reference
+ * tree).  Plain pointers and sizes only; no C++ or torch types.  All functions return
+ * GBD_PCG_OK (0) or a negative gbd_pcg_status; none of them ever calls exit() (the reference
+ * aborts through gpuErrchk, GBD-PCG/include/gpuassert.cuh:5-14).
+ *
+ * Data layout (identical to the reference, GBD-PCG/include/utils.cuh:58-84,98-161):
+ *   S, Pinv : [N][3][n][n]   tile t in {0:left, 1:diag, 2:right} of block row b at
+ *                            b*3n^2 + t*n^2, COLUMN-major inside a tile (elem(r,c) at c*n + r).
+ *                            Tiles (0,0) and (N-1,2) are padding: never read, may be uninitialised.
+ *   gamma, lambda, r, p : [N*n]
+ * Batched variants prepend a [batch] dimension to every array.
+ *
+ * Results are bit-identical to the reference kernel pcg<T,n,N> (same floating-point operation
+ * order: sequential FMA over the band row, GLASS halving trees for the dots, IEEE division).
+ */
+#ifndef GBD_PCG_H
+#define GBD_PCG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum gbd_pcg_status {
+    GBD_PCG_OK = 0,
+    GBD_PCG_ERR_UNSUPPORTED = -1, /* (n, N, dtype) has no compiled kernel; see gbd_pcg_supported() */
+    GBD_PCG_ERR_BADARG = -2,      /* null pointer, N < 2, batch == 0, ... */
+    GBD_PCG_ERR_CUDA = -3,        /* a CUDA call failed; code in gbd_pcg_last_cuda_error() */
+    GBD_PCG_ERR_NODEVICE = -4     /* no CUDA device / driver: there is NO CPU fallback */
+} gbd_pcg_status;
+
+#define GBD_PCG_ABI_VERSION 1
+
+int gbd_pcg_abi_version(void);
+const char *gbd_pcg_strerror(int status);
+int gbd_pcg_last_cuda_error(void); /* cudaError_t of the last failing CUDA call on this thread */
+
+/* Which (state_size n, knot_points N) pairs are compiled in.  The reference fixes (n, N) at compile
+ * time through the STATE_SIZE / KNOT_POINTS macros (GBD-PCG/include/constants.cuh:5-11,
+ * interface.cuh:110); here the pairs are enumerated at run time. */
+int gbd_pcg_supported(uint32_t n, uint32_t N, int is_f64);
+int gbd_pcg_num_variants(void);
+int gbd_pcg_variant_at(int i, uint32_t *n, uint32_t *N, uint32_t *cluster, int *regs, int *is_f64,
+                       uint32_t *threads, size_t *smem_bytes);
+
+/* Tuning knob: pick the cluster size (CTAs per system) / tile residency used for (n, N).
+ * cluster = 0 and regs = -1 restore the built-in default. */
+int gbd_pcg_set_tuning(uint32_t n, uint32_t N, int is_f64, uint32_t cluster, int regs);
+
+/*
+ * One solve, device pointers, asynchronous on `stream` (a cudaStream_t, or NULL).
+ * Replaces the kernel launch at include/pcg/sqp.cuh:129-151,230
+ *   cudaLaunchCooperativeKernel(pcg<T,STATE_SIZE,KNOT_POINTS>, knot_points, PCG_NUM_THREADS, args, smem)
+ * with the kernel's own 12-argument list (GBD-PCG/include/pcg.cuh:56-68), plus n, N and the stream.
+ *   d_lambda  in: initial guess, out: solution
+ *   d_r, d_p  caller-owned scratch of N*n; on return hold the final residual / direction, as the
+ *             reference leaves them (either may be NULL)
+ *   d_v_temp, d_eta_new_temp  caller-owned scratch of N in the reference; unused here, may be NULL
+ *   d_iters   1 x uint32: iterations run (k+1 when iteration k passed the exit test, max_iter otherwise)
+ *   d_max_iter_exit  1 byte (the reference's bool): 1 when the iteration cap was hit
+ */
+int gbd_pcg_solve_f32(uint32_t n, uint32_t N, const float *d_S, const float *d_Pinv, const float *d_gamma,
+                      float *d_lambda, float *d_r, float *d_p, float *d_v_temp, float *d_eta_new_temp,
+                      uint32_t *d_iters, uint8_t *d_max_iter_exit, uint32_t max_iter, float exit_tol,
+                      void *stream);
+int gbd_pcg_solve_f64(uint32_t n, uint32_t N, const double *d_S, const double *d_Pinv, const double *d_gamma,
+                      double *d_lambda, double *d_r, double *d_p, double *d_v_temp, double *d_eta_new_temp,
+                      uint32_t *d_iters, uint8_t *d_max_iter_exit, uint32_t max_iter, double exit_tol,
+                      void *stream);
+
+/*
+ * The reference's "SQP linsys" window, include/pcg/sqp.cuh:224-241: device sync, launch, blocking
+ * read-back of the iteration count and the exit flag, device sync.  Returns the two host values and
+ * (if elapsed_us != NULL) the wall time of the window measured the way the reference measures it
+ * (clock_gettime(CLOCK_MONOTONIC) around it).
+ */
+int gbd_pcg_linsys_f32(uint32_t n, uint32_t N, const float *d_S, const float *d_Pinv, const float *d_gamma,
+                       float *d_lambda, float *d_r, float *d_p, uint32_t *d_iters, uint8_t *d_max_iter_exit,
+                       uint32_t max_iter, float exit_tol, uint32_t *h_iters, uint8_t *h_max_iter_exit,
+                       double *elapsed_us);
+
+/*
+ * Many independent systems in one launch (new capability; the reference has no batched path).
+ * Arrays carry a leading [batch] dimension; d_iters / d_max_iter_exit have `batch` entries.
+ * System i is solved exactly as gbd_pcg_solve_f32 would solve it alone (bit-identical).
+ * d_r / d_p may be NULL.
+ */
+int gbd_pcg_solve_batched_f32(uint32_t n, uint32_t N, uint32_t batch, const float *d_S, const float *d_Pinv,
+                              const float *d_gamma, float *d_lambda, float *d_r, float *d_p,
+                              uint32_t *d_iters, uint8_t *d_max_iter_exit, uint32_t max_iter, float exit_tol,
+                              void *stream);
+
+/*
+ * Host-buffer path.  Replaces solvePCG<T>(h_S, h_gamma, h_lambda, stateSize, knotPoints, config)
+ * (GBD-PCG/include/interface.cuh:24-89): copies S, Pinv, gamma, lambda to the device, solves,
+ * copies lambda back.  Unlike the reference it (a) takes the preconditioner explicitly (the
+ * reference leaves d_Pinv uninitialised, interface.cuh:45-46), (b) returns the real iteration
+ * count and exit flag (the reference returns the constant 1, interface.cuh:88), and (c) keeps its
+ * device buffers and stream in a reusable plan instead of cudaMalloc/cudaFree per call.
+ * Host buffers may be pageable or pinned; `batch` systems are solved per call.
+ */
+typedef struct gbd_pcg_plan gbd_pcg_plan;
+int gbd_pcg_plan_create(uint32_t n, uint32_t N, uint32_t batch, int is_f64, gbd_pcg_plan **out);
+int gbd_pcg_plan_destroy(gbd_pcg_plan *plan);
+int gbd_pcg_plan_solve_host_f32(gbd_pcg_plan *plan, const float *h_S, const float *h_Pinv, const float *h_gamma,
+                                float *h_lambda, uint32_t max_iter, float exit_tol, uint32_t *h_iters,
+                                uint8_t *h_max_iter_exit);
+int gbd_pcg_plan_solve_host_f64(gbd_pcg_plan *plan, const double *h_S, const double *h_Pinv,
+                                const double *h_gamma, double *h_lambda, uint32_t max_iter, double exit_tol,
+                                uint32_t *h_iters, uint8_t *h_max_iter_exit);
+
+/* Number of kernels this library has launched in this process (for bench.py's gpu_launches). */
+uint64_t gbd_pcg_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GBD_PCG_H */

@@ -1,0 +1,344 @@
+// gbd_capi.cu -- C ABI of libgbdpcg.so (declared in include/gbd_pcg.h): variant table, launch
+// configuration (cluster dims, opt-in shared memory), device-pointer / linsys-window / batched /
+// host-buffer entry points.  There is no CPU fallback anywhere in this file: without a CUDA
+// device every compute entry returns GBD_PCG_ERR_NODEVICE / GBD_PCG_ERR_CUDA.
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <mutex>
+#include <vector>
+
+#include "../../include/gbd_pcg.h"
+#include "gbd_cluster_pcg.cuh"
+
+namespace {
+
+using namespace gbd;
+
+struct Variant {
+    uint32_t n, N, C;
+    bool regs, f64;
+    uint32_t nt;
+    size_t smem;
+    const void *kernel;
+    bool prepared;
+};
+
+template <typename T, uint32_t n, uint32_t N, uint32_t C, bool REGS>
+Variant make_variant()
+{
+    using K = ClusterPcg<T, n, N, C, REGS>;
+    return Variant{n, N, C, REGS, sizeof(T) == 8, K::NT, K::SMEM_BYTES,
+                   (const void *)pcg_cluster_kernel<T, n, N, C, REGS>, false};
+}
+
+// (n, N) pairs: IIWA (n=14) at the reference's horizons (include/common/settings.cuh:123-138) plus
+// small systems for tests (n=2,N=3 is the GBD-PCG demo, GBD-PCG/examples/pcg_solve.cu:14-25).
+// The FIRST variant listed for an (n, N, dtype) is the default.
+std::vector<Variant> &variants()
+{
+    static std::vector<Variant> v = {
+        make_variant<float, 14, 128, 8, true>(),  make_variant<float, 14, 128, 16, true>(),
+        make_variant<float, 14, 128, 4, true>(),  make_variant<float, 14, 128, 8, false>(),
+        make_variant<float, 14, 32, 4, true>(),   make_variant<float, 14, 32, 8, true>(),
+        make_variant<float, 14, 32, 2, true>(),   make_variant<float, 14, 32, 1, true>(),
+        make_variant<float, 14, 32, 8, false>(),
+        make_variant<float, 14, 64, 8, true>(),   make_variant<float, 14, 64, 4, true>(),
+        make_variant<float, 14, 256, 8, true>(),  make_variant<float, 14, 256, 16, true>(),
+        make_variant<float, 14, 512, 16, true>(), make_variant<float, 14, 512, 16, false>(),
+        make_variant<float, 14, 16, 4, true>(),   make_variant<float, 14, 8, 8, true>(),
+        make_variant<float, 14, 8, 2, true>(),
+        make_variant<float, 6, 12, 4, true>(),    make_variant<float, 6, 12, 1, true>(),
+        make_variant<float, 6, 12, 2, false>(),
+        make_variant<float, 2, 3, 1, true>(),     make_variant<float, 2, 3, 3, false>(),
+        make_variant<double, 14, 128, 8, false>(), make_variant<double, 14, 32, 8, false>(),
+        make_variant<double, 6, 12, 4, false>(),  make_variant<double, 2, 3, 1, false>(),
+    };
+    return v;
+}
+
+struct Tuning { uint32_t n, N; bool f64; uint32_t C; int regs; };
+std::vector<Tuning> &tunings() { static std::vector<Tuning> t; return t; }
+std::mutex g_mu;
+std::atomic<uint64_t> g_launches{0};
+thread_local int tl_cuda_err = 0;
+
+int cuda_fail(cudaError_t e)
+{
+    tl_cuda_err = (int)e;
+    cudaGetLastError();   // clear the sticky-less error state
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return GBD_PCG_ERR_NODEVICE;
+    return GBD_PCG_ERR_CUDA;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(e_); } while (0)
+
+Variant *find_variant(uint32_t n, uint32_t N, bool f64)
+{
+    uint32_t wantC = 0; int wantRegs = -1;
+    for (auto &t : tunings()) if (t.n == n && t.N == N && t.f64 == f64) { wantC = t.C; wantRegs = t.regs; }
+    Variant *first = nullptr;
+    for (auto &v : variants()) {
+        if (v.n != n || v.N != N || v.f64 != f64) continue;
+        if (!first) first = &v;
+        if ((wantC == 0 || v.C == wantC) && (wantRegs < 0 || (int)v.regs == wantRegs)) return &v;
+    }
+    return (wantC == 0 && wantRegs < 0) ? first : nullptr;
+}
+
+int prepare(Variant &v)
+{
+    if (v.prepared) return GBD_PCG_OK;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (v.prepared) return GBD_PCG_OK;
+    if (v.smem > 48 * 1024) CK(cudaFuncSetAttribute(v.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem));
+    if (v.C > 8) CK(cudaFuncSetAttribute(v.kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    v.prepared = true;
+    return GBD_PCG_OK;
+}
+
+// how many clusters of this variant the device can hold at once (persistent-grid size for batches)
+int max_clusters(Variant &v, int *out)
+{
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[1];
+    cfg.gridDim = dim3(v.C * 1024);
+    cfg.blockDim = dim3(v.nt);
+    cfg.dynamicSmemBytes = v.smem;
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = v.C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int nc = 0;
+    CK(cudaOccupancyMaxActiveClusters(&nc, v.kernel, &cfg));
+    *out = nc;
+    return GBD_PCG_OK;
+}
+
+template <typename T>
+int launch(uint32_t n, uint32_t N, uint32_t batch, const T *S, const T *P, const T *g, T *lam, T *r, T *p,
+           uint32_t *iters, uint8_t *flag, uint32_t max_iter, T tol, cudaStream_t st)
+{
+    if (!S || !P || !g || !lam || !iters || !flag || batch == 0 || N < 2 || n == 0) return GBD_PCG_ERR_BADARG;
+    Variant *v = find_variant(n, N, sizeof(T) == 8);
+    if (!v) return GBD_PCG_ERR_UNSUPPORTED;
+    int rc = prepare(*v);
+    if (rc) return rc;
+
+    uint32_t nclusters = batch;
+    if (batch > 1) {
+        static thread_local const void *cached_k = nullptr;
+        static thread_local int cached_nc = 0;
+        if (cached_k != v->kernel) {
+            int nc = 0;
+            rc = max_clusters(*v, &nc);
+            if (rc) return rc;
+            cached_k = v->kernel; cached_nc = nc > 0 ? nc : 1;
+        }
+        if (nclusters > (uint32_t)cached_nc) nclusters = (uint32_t)cached_nc;
+    }
+    PcgArgs<T> a;
+    a.S = S; a.Pinv = P; a.gamma = g; a.lambda = lam; a.r_out = r; a.p_out = p;
+    a.iters = iters; a.max_iter_exit = flag; a.batch = batch; a.max_iter = max_iter; a.exit_tol = tol;
+    a.use_tma = (((uintptr_t)S | (uintptr_t)P) & 15u) == 0 ? 1u : 0u;
+
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[1];
+    cfg.gridDim = dim3(nclusters * v->C);
+    cfg.blockDim = dim3(v->nt);
+    cfg.dynamicSmemBytes = v->smem;
+    cfg.stream = st;
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = v->C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    void *args[] = {&a};
+    CK(cudaLaunchKernelExC(&cfg, v->kernel, args));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return GBD_PCG_OK;
+}
+
+}  // namespace
+
+struct gbd_pcg_plan {
+    uint32_t n, N, batch;
+    bool f64;
+    size_t esz;
+    void *dS, *dP, *dg, *dl;
+    uint32_t *d_iters;
+    uint8_t *d_flag;
+    cudaStream_t st;
+};
+
+extern "C" {
+
+int gbd_pcg_abi_version(void) { return GBD_PCG_ABI_VERSION; }
+
+const char *gbd_pcg_strerror(int s)
+{
+    switch (s) {
+        case GBD_PCG_OK: return "ok";
+        case GBD_PCG_ERR_UNSUPPORTED: return "no kernel compiled for this (state_size, knot_points, dtype)";
+        case GBD_PCG_ERR_BADARG: return "bad argument";
+        case GBD_PCG_ERR_CUDA: return "CUDA error (see gbd_pcg_last_cuda_error)";
+        case GBD_PCG_ERR_NODEVICE: return "no CUDA device (this library has no CPU fallback)";
+        default: return "unknown status";
+    }
+}
+
+int gbd_pcg_last_cuda_error(void) { return tl_cuda_err; }
+
+int gbd_pcg_supported(uint32_t n, uint32_t N, int is_f64)
+{
+    for (auto &v : variants()) if (v.n == n && v.N == N && v.f64 == (is_f64 != 0)) return 1;
+    return 0;
+}
+
+int gbd_pcg_num_variants(void) { return (int)variants().size(); }
+
+int gbd_pcg_variant_at(int i, uint32_t *n, uint32_t *N, uint32_t *cluster, int *regs, int *is_f64,
+                       uint32_t *threads, size_t *smem_bytes)
+{
+    if (i < 0 || i >= (int)variants().size()) return GBD_PCG_ERR_BADARG;
+    const Variant &v = variants()[i];
+    if (n) *n = v.n;
+    if (N) *N = v.N;
+    if (cluster) *cluster = v.C;
+    if (regs) *regs = v.regs;
+    if (is_f64) *is_f64 = v.f64;
+    if (threads) *threads = v.nt;
+    if (smem_bytes) *smem_bytes = v.smem;
+    return GBD_PCG_OK;
+}
+
+int gbd_pcg_set_tuning(uint32_t n, uint32_t N, int is_f64, uint32_t cluster, int regs)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto &t = tunings();
+    for (size_t i = 0; i < t.size(); ++i)
+        if (t[i].n == n && t[i].N == N && t[i].f64 == (is_f64 != 0)) { t.erase(t.begin() + i); break; }
+    if (cluster == 0 && regs < 0) return GBD_PCG_OK;
+    bool ok = false;
+    for (auto &v : variants())
+        if (v.n == n && v.N == N && v.f64 == (is_f64 != 0) && (cluster == 0 || v.C == cluster) && (regs < 0 || (int)v.regs == regs)) ok = true;
+    if (!ok) return GBD_PCG_ERR_UNSUPPORTED;
+    t.push_back(Tuning{n, N, is_f64 != 0, cluster, regs});
+    return GBD_PCG_OK;
+}
+
+int gbd_pcg_solve_f32(uint32_t n, uint32_t N, const float *d_S, const float *d_Pinv, const float *d_gamma,
+                      float *d_lambda, float *d_r, float *d_p, float *, float *, uint32_t *d_iters,
+                      uint8_t *d_max_iter_exit, uint32_t max_iter, float exit_tol, void *stream)
+{
+    return launch<float>(n, N, 1, d_S, d_Pinv, d_gamma, d_lambda, d_r, d_p, d_iters, d_max_iter_exit, max_iter,
+                         exit_tol, (cudaStream_t)stream);
+}
+
+int gbd_pcg_solve_f64(uint32_t n, uint32_t N, const double *d_S, const double *d_Pinv, const double *d_gamma,
+                      double *d_lambda, double *d_r, double *d_p, double *, double *, uint32_t *d_iters,
+                      uint8_t *d_max_iter_exit, uint32_t max_iter, double exit_tol, void *stream)
+{
+    return launch<double>(n, N, 1, d_S, d_Pinv, d_gamma, d_lambda, d_r, d_p, d_iters, d_max_iter_exit, max_iter,
+                          exit_tol, (cudaStream_t)stream);
+}
+
+int gbd_pcg_linsys_f32(uint32_t n, uint32_t N, const float *d_S, const float *d_Pinv, const float *d_gamma,
+                       float *d_lambda, float *d_r, float *d_p, uint32_t *d_iters, uint8_t *d_max_iter_exit,
+                       uint32_t max_iter, float exit_tol, uint32_t *h_iters, uint8_t *h_max_iter_exit,
+                       double *elapsed_us)
+{
+    if (!h_iters || !h_max_iter_exit) return GBD_PCG_ERR_BADARG;
+    timespec t0, t1;
+    CK(cudaDeviceSynchronize());
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    int rc = launch<float>(n, N, 1, d_S, d_Pinv, d_gamma, d_lambda, d_r, d_p, d_iters, d_max_iter_exit, max_iter,
+                           exit_tol, (cudaStream_t)0);
+    if (rc) return rc;
+    CK(cudaMemcpy(h_iters, d_iters, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(h_max_iter_exit, d_max_iter_exit, sizeof(uint8_t), cudaMemcpyDeviceToHost));
+    CK(cudaDeviceSynchronize());
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    if (elapsed_us) *elapsed_us = 1e6 * (double)(t1.tv_sec - t0.tv_sec) + 1e-3 * (double)(t1.tv_nsec - t0.tv_nsec);
+    return GBD_PCG_OK;
+}
+
+int gbd_pcg_solve_batched_f32(uint32_t n, uint32_t N, uint32_t batch, const float *d_S, const float *d_Pinv,
+                              const float *d_gamma, float *d_lambda, float *d_r, float *d_p, uint32_t *d_iters,
+                              uint8_t *d_max_iter_exit, uint32_t max_iter, float exit_tol, void *stream)
+{
+    return launch<float>(n, N, batch, d_S, d_Pinv, d_gamma, d_lambda, d_r, d_p, d_iters, d_max_iter_exit, max_iter,
+                         exit_tol, (cudaStream_t)stream);
+}
+
+int gbd_pcg_plan_create(uint32_t n, uint32_t N, uint32_t batch, int is_f64, gbd_pcg_plan **out)
+{
+    if (!out || batch == 0) return GBD_PCG_ERR_BADARG;
+    if (!gbd_pcg_supported(n, N, is_f64)) return GBD_PCG_ERR_UNSUPPORTED;
+    gbd_pcg_plan *p = (gbd_pcg_plan *)calloc(1, sizeof(gbd_pcg_plan));
+    p->n = n; p->N = N; p->batch = batch; p->f64 = is_f64 != 0; p->esz = is_f64 ? 8 : 4;
+    const size_t mat = (size_t)3 * n * n * N * batch * p->esz, vec = (size_t)n * N * batch * p->esz;
+    cudaError_t e;
+    if ((e = cudaStreamCreateWithFlags(&p->st, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaMalloc(&p->dS, mat)) != cudaSuccess || (e = cudaMalloc(&p->dP, mat)) != cudaSuccess ||
+        (e = cudaMalloc(&p->dg, vec)) != cudaSuccess || (e = cudaMalloc(&p->dl, vec)) != cudaSuccess ||
+        (e = cudaMalloc((void **)&p->d_iters, sizeof(uint32_t) * batch)) != cudaSuccess ||
+        (e = cudaMalloc((void **)&p->d_flag, batch)) != cudaSuccess) {
+        gbd_pcg_plan_destroy(p);
+        return cuda_fail(e);
+    }
+    *out = p;
+    return GBD_PCG_OK;
+}
+
+int gbd_pcg_plan_destroy(gbd_pcg_plan *p)
+{
+    if (!p) return GBD_PCG_OK;
+    cudaFree(p->dS); cudaFree(p->dP); cudaFree(p->dg); cudaFree(p->dl); cudaFree(p->d_iters); cudaFree(p->d_flag);
+    if (p->st) cudaStreamDestroy(p->st);
+    free(p);
+    return GBD_PCG_OK;
+}
+
+}  // extern "C"
+
+namespace {
+template <typename T>
+int plan_solve_host(gbd_pcg_plan *p, const T *hS, const T *hP, const T *hg, T *hl, uint32_t max_iter, T tol,
+                    uint32_t *h_iters, uint8_t *h_flag)
+{
+    if (!p || !hS || !hP || !hg || !hl || !h_iters || !h_flag) return GBD_PCG_ERR_BADARG;
+    if (p->f64 != (sizeof(T) == 8)) return GBD_PCG_ERR_BADARG;
+    const size_t mat = (size_t)3 * p->n * p->n * p->N * p->batch * sizeof(T), vec = (size_t)p->n * p->N * p->batch * sizeof(T);
+    CK(cudaMemcpyAsync(p->dS, hS, mat, cudaMemcpyHostToDevice, p->st));
+    CK(cudaMemcpyAsync(p->dP, hP, mat, cudaMemcpyHostToDevice, p->st));
+    CK(cudaMemcpyAsync(p->dg, hg, vec, cudaMemcpyHostToDevice, p->st));
+    CK(cudaMemcpyAsync(p->dl, hl, vec, cudaMemcpyHostToDevice, p->st));
+    int rc = launch<T>(p->n, p->N, p->batch, (const T *)p->dS, (const T *)p->dP, (const T *)p->dg, (T *)p->dl,
+                       (T *)nullptr, (T *)nullptr, p->d_iters, p->d_flag, max_iter, tol, p->st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(hl, p->dl, vec, cudaMemcpyDeviceToHost, p->st));
+    CK(cudaMemcpyAsync(h_iters, p->d_iters, sizeof(uint32_t) * p->batch, cudaMemcpyDeviceToHost, p->st));
+    CK(cudaMemcpyAsync(h_flag, p->d_flag, p->batch, cudaMemcpyDeviceToHost, p->st));
+    CK(cudaStreamSynchronize(p->st));
+    return GBD_PCG_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int gbd_pcg_plan_solve_host_f32(gbd_pcg_plan *plan, const float *h_S, const float *h_Pinv, const float *h_gamma,
+                                float *h_lambda, uint32_t max_iter, float exit_tol, uint32_t *h_iters,
+                                uint8_t *h_max_iter_exit)
+{
+    return plan_solve_host<float>(plan, h_S, h_Pinv, h_gamma, h_lambda, max_iter, exit_tol, h_iters, h_max_iter_exit);
+}
+
+int gbd_pcg_plan_solve_host_f64(gbd_pcg_plan *plan, const double *h_S, const double *h_Pinv, const double *h_gamma,
+                                double *h_lambda, uint32_t max_iter, double exit_tol, uint32_t *h_iters,
+                                uint8_t *h_max_iter_exit)
+{
+    return plan_solve_host<double>(plan, h_S, h_Pinv, h_gamma, h_lambda, max_iter, exit_tol, h_iters, h_max_iter_exit);
+}
+
+uint64_t gbd_pcg_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+}  // extern "C"

@@ -1,0 +1,153 @@
+"""Host-side mirror of the reference's GBD-PCG call surface, over the C ABI (include/gbd_pcg.h).
+
+Names, argument meaning and outputs follow ``GBD-PCG/include/interface.cuh`` and ``types.cuh``:
+
+* :class:`PcgConfig`      <- ``pcg_config<T>``  (types.cuh:18-35, defaults constants.cuh:14-20)
+* :func:`solvePCG`        <- ``solvePCG(h_S, h_gamma, h_lambda, stateSize, knotPoints, config)``
+  (interface.cuh:24-89; host buffers)
+* :func:`solvePCG_device` <- ``solvePCG(state_size, knot_points, d_S, d_Pinv, ..., config)``
+  (interface.cuh:92-144; device buffers, returns the iteration count)
+* :func:`pcg_launch`      <- the kernel launch in the SQP loop (include/pcg/sqp.cuh:230)
+* :func:`linsys_window`   <- the timed "SQP linsys" window (include/pcg/sqp.cuh:224-241)
+* :func:`solve_batched`   <- new: many independent systems per launch
+
+Device buffers are ``torch`` CUDA tensors (torch is only the allocator / stream provider here);
+host buffers are numpy arrays.  Nothing in this module computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _capi
+
+
+@dataclass
+class PcgConfig:
+    pcg_exit_tol: float = 1e-6
+    pcg_max_iter: int = 25
+    pcg_grid: int = 128
+    pcg_block: int = 64
+    empty_pinv: int = 1
+
+
+def _ptr(t):
+    return 0 if t is None else int(t.data_ptr())
+
+
+def _stream(stream):
+    if stream is None:
+        import torch
+        return int(torch.cuda.current_stream().cuda_stream)
+    return int(getattr(stream, "cuda_stream", stream))
+
+
+def _check_dev(n, N, batch, d_S, d_Pinv, d_gamma, d_lambda):
+    import torch
+    dt = d_S.dtype
+    if dt not in (torch.float32, torch.float64):
+        raise TypeError("GBD-PCG computes in float32 or float64")
+    for name, t, cnt in (("d_S", d_S, 3 * n * n * N * batch), ("d_Pinv", d_Pinv, 3 * n * n * N * batch),
+                         ("d_gamma", d_gamma, n * N * batch), ("d_lambda", d_lambda, n * N * batch)):
+        if not t.is_cuda or not t.is_contiguous() or t.dtype != dt or t.numel() != cnt:
+            raise ValueError(f"{name}: expected a contiguous CUDA {dt} tensor of {cnt} elements")
+    return dt == torch.float64
+
+
+def pcg_launch(state_size, knot_points, d_S, d_Pinv, d_gamma, d_lambda, d_r, d_p, d_v_temp, d_eta_new_temp,
+               d_iters, d_max_iter_exit, max_iter, exit_tol, stream=None):
+    """Asynchronous solve; the 12 kernel arguments of pcg<T,n,N> (pcg.cuh:56-68) plus n, N, stream."""
+    f64 = _check_dev(state_size, knot_points, 1, d_S, d_Pinv, d_gamma, d_lambda)
+    fn = _capi.lib().gbd_pcg_solve_f64 if f64 else _capi.lib().gbd_pcg_solve_f32
+    _capi.check(fn(state_size, knot_points, _ptr(d_S), _ptr(d_Pinv), _ptr(d_gamma), _ptr(d_lambda), _ptr(d_r),
+                   _ptr(d_p), _ptr(d_v_temp), _ptr(d_eta_new_temp), _ptr(d_iters), _ptr(d_max_iter_exit),
+                   int(max_iter), float(exit_tol), _stream(stream)), "gbd_pcg_solve")
+
+
+def solvePCG_device(state_size, knot_points, d_S, d_Pinv, d_gamma, d_lambda, d_r, d_p, d_v_temp, d_eta_new_temp,
+                    config: PcgConfig, return_flag: bool = False):
+    """interface.cuh:92-144: allocates d_pcg_iters / d_pcg_exit, launches, reads the count back."""
+    import torch
+    d_iters = torch.zeros(1, dtype=torch.int32, device=d_S.device)
+    d_flag = torch.zeros(1, dtype=torch.uint8, device=d_S.device)
+    pcg_launch(state_size, knot_points, d_S, d_Pinv, d_gamma, d_lambda, d_r, d_p, d_v_temp, d_eta_new_temp,
+               d_iters, d_flag, config.pcg_max_iter, config.pcg_exit_tol)
+    iters = int(d_iters.item())
+    return (iters, bool(d_flag.item())) if return_flag else iters
+
+
+def linsys_window(state_size, knot_points, d_S, d_Pinv, d_gamma, d_lambda, d_r, d_p, d_iters, d_max_iter_exit,
+                  max_iter, exit_tol):
+    """sqp.cuh:224-241: sync, launch, two blocking D2H reads, sync.  Returns (iters, flag, microseconds)."""
+    if _check_dev(state_size, knot_points, 1, d_S, d_Pinv, d_gamma, d_lambda):
+        raise TypeError("linsys_window is float32 only")
+    it, fl, us = C.c_uint32(0), C.c_uint8(0), C.c_double(0)
+    _capi.check(_capi.lib().gbd_pcg_linsys_f32(state_size, knot_points, _ptr(d_S), _ptr(d_Pinv), _ptr(d_gamma),
+                                               _ptr(d_lambda), _ptr(d_r), _ptr(d_p), _ptr(d_iters),
+                                               _ptr(d_max_iter_exit), int(max_iter), float(exit_tol),
+                                               C.byref(it), C.byref(fl), C.byref(us)), "gbd_pcg_linsys_f32")
+    return int(it.value), bool(fl.value), float(us.value)
+
+
+def solve_batched(state_size, knot_points, batch, d_S, d_Pinv, d_gamma, d_lambda, d_iters, d_max_iter_exit,
+                  max_iter, exit_tol, d_r=None, d_p=None, stream=None):
+    if _check_dev(state_size, knot_points, batch, d_S, d_Pinv, d_gamma, d_lambda):
+        raise TypeError("solve_batched is float32 only")
+    _capi.check(_capi.lib().gbd_pcg_solve_batched_f32(state_size, knot_points, batch, _ptr(d_S), _ptr(d_Pinv),
+                                                      _ptr(d_gamma), _ptr(d_lambda), _ptr(d_r), _ptr(d_p),
+                                                      _ptr(d_iters), _ptr(d_max_iter_exit), int(max_iter),
+                                                      float(exit_tol), _stream(stream)), "gbd_pcg_solve_batched_f32")
+
+
+class HostPlan:
+    """Reusable device workspace for host-buffer solves (gbd_pcg_plan_*)."""
+
+    def __init__(self, state_size: int, knot_points: int, batch: int = 1, dtype=np.float32):
+        self.n, self.N, self.batch = state_size, knot_points, batch
+        self.dtype = np.dtype(dtype)
+        if self.dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
+            raise TypeError("float32 or float64")
+        self._h = C.c_void_p()
+        _capi.check(_capi.lib().gbd_pcg_plan_create(state_size, knot_points, batch, int(self.dtype == np.float64),
+                                                    C.byref(self._h)), "gbd_pcg_plan_create")
+
+    def close(self):
+        if self._h:
+            _capi.lib().gbd_pcg_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def solve(self, h_S, h_Pinv, h_gamma, h_lambda, max_iter, exit_tol):
+        """h_lambda is updated in place.  Returns (iters[batch], max_iter_exit[batch])."""
+        n, N, B = self.n, self.N, self.batch
+        for name, a, cnt in (("h_S", h_S, 3 * n * n * N * B), ("h_Pinv", h_Pinv, 3 * n * n * N * B),
+                             ("h_gamma", h_gamma, n * N * B), ("h_lambda", h_lambda, n * N * B)):
+            if not isinstance(a, np.ndarray) or a.dtype != self.dtype or not a.flags.c_contiguous or a.size != cnt:
+                raise ValueError(f"{name}: expected a C-contiguous {self.dtype} ndarray of {cnt} elements")
+        iters = np.zeros(B, np.uint32)
+        flags = np.zeros(B, np.uint8)
+        fn = (_capi.lib().gbd_pcg_plan_solve_host_f64 if self.dtype == np.float64
+              else _capi.lib().gbd_pcg_plan_solve_host_f32)
+        _capi.check(fn(self._h, h_S.ctypes.data, h_Pinv.ctypes.data, h_gamma.ctypes.data, h_lambda.ctypes.data,
+                       int(max_iter), float(exit_tol), iters.ctypes.data, flags.ctypes.data), "gbd_pcg_plan_solve_host")
+        return iters, flags.astype(bool)
+
+
+_plans: dict = {}
+
+
+def solvePCG(h_S, h_Pinv, h_gamma, h_lambda, stateSize, knotPoints, config: PcgConfig, return_flag: bool = False):
+    """interface.cuh:24-89 with the preconditioner made explicit; h_lambda is overwritten with the solution."""
+    key = (stateSize, knotPoints, 1, np.dtype(h_S.dtype).str)
+    plan = _plans.get(key)
+    if plan is None:
+        plan = _plans[key] = HostPlan(stateSize, knotPoints, 1, h_S.dtype)
+    iters, flags = plan.solve(h_S, h_Pinv, h_gamma, h_lambda, config.pcg_max_iter, config.pcg_exit_tol)
+    return (int(iters[0]), bool(flags[0])) if return_flag else int(iters[0])
