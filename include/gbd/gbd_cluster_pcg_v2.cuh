@@ -1,0 +1,360 @@
+// gbd_cluster_pcg_v2.cuh -- cluster-resident GBD-PCG, second generation (n <= 32).
+//
+// Same contract and the same floating-point operation order as gbd_cluster_pcg.cuh (and therefore
+// as the reference pcg<T,n,N>, GBD-PCG/include/pcg.cuh:54-218); what changes is how the two
+// per-iteration synchronisation points are implemented:
+//
+//  * no barrier.cluster in the iteration loop.  Every cross-CTA datum (a knot row's dot partial for
+//    all C CTAs, a boundary row of upsilon / r~ for the neighbour) is pushed with
+//    `st.async ... mbarrier::complete_tx::bytes` straight into the consumer's shared memory and
+//    counted on the consumer's mbarrier; the consumer arms the expected byte count once per phase
+//    and waits on its own barrier.  Data and signal travel together, no release/acquire fence, no
+//    L1 invalidation (barrier.cluster costs ~380 cycles + CCTL.IVALL on this part).
+//  * each knot row sits in one half-warp (16 lanes, n <= 16) or one warp (n <= 32): the per-knot
+//    GLASS tree over the n products is done with width-limited shuffles, no smem round trip and no
+//    __syncthreads; C lanes of the group then fan the partial out to the C CTAs in parallel.
+//  * partials are stored transposed so the N-way tree starts with one 128-bit load per lane.
+//  * vector windows are padded to a multiple of 4 elements per knot row: 128-bit smem loads.
+//  * one __syncthreads per half iteration (own p / r rows visible before the band-row chains).
+#pragma once
+#include "gbd_cluster_pcg.cuh"
+
+namespace gbd {
+
+__device__ __forceinline__ void st_async(uint32_t addr, float v, uint32_t mbar)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];" ::"r"(addr), "f"(v),
+                 "r"(mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void st_async(uint32_t addr, double v, uint32_t mbar)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f64 [%0], %1, [%2];" ::"r"(addr), "d"(v),
+                 "r"(mbar)
+                 : "memory");
+}
+
+// GLASS tree over CNT values held one per lane in lanes 0..CNT-1 of a G-lane group; total in lane 0.
+template <typename T, uint32_t CNT, uint32_t G>
+__device__ __forceinline__ T glass_tree_shfl(T x, uint32_t lane_in_group)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    uint32_t s = CNT;
+#pragma unroll
+    for (int lvl = 0; lvl < 8; ++lvl) {
+        if (s > 3) {
+            const uint32_t odd = s & 1u;
+            s = (s - odd) / 2;
+            const T y = __shfl_down_sync(FULL, x, s, G);
+            T z = T(0);
+            if (odd) z = __shfl_sync(FULL, x, 2 * s, G);      // pre-level value of element 2s (odd fix-up)
+            x = add_rn(x, y);
+            if (odd && lane_in_group == 0) x = add_rn(x, z);
+        }
+    }
+    const T y1 = __shfl_sync(FULL, x, 1, G), y2 = __shfl_sync(FULL, x, 2, G);
+    if (lane_in_group == 0) {
+        if (s >= 2) x = add_rn(x, y1);
+        if (s >= 3) x = add_rn(x, y2);
+    }
+    return x;
+}
+
+template <uint32_t CNT>
+__host__ __device__ constexpr uint32_t part_index(uint32_t b)
+{
+    return (is_pow2<CNT>::value && CNT >= 32) ? (b % 32) * (CNT / 32) + b / 32 : b;
+}
+
+// N-way GLASS tree over partials stored with part_index(); every lane returns the total.
+template <typename T, uint32_t CNT>
+__device__ __forceinline__ T glass_tree_part(const T *part)
+{
+    if constexpr (is_pow2<CNT>::value && CNT >= 32) {
+        constexpr uint32_t PER = CNT / 32;
+        const uint32_t lane = threadIdx.x & 31u;
+        T v[PER];
+        if constexpr (sizeof(T) == 4 && PER % 4 == 0) {
+#pragma unroll
+            for (uint32_t q = 0; q < PER / 4; ++q) {
+                const float4 f = reinterpret_cast<const float4 *>(part)[lane * (PER / 4) + q];
+                v[4 * q] = f.x; v[4 * q + 1] = f.y; v[4 * q + 2] = f.z; v[4 * q + 3] = f.w;
+            }
+        } else {
+#pragma unroll
+            for (uint32_t q = 0; q < PER; ++q) v[q] = part[lane * PER + q];
+        }
+#pragma unroll
+        for (uint32_t h = PER / 2; h >= 1; h /= 2) {
+#pragma unroll
+            for (uint32_t q = 0; q < PER / 2; ++q)
+                if (q < h) v[q] = add_rn(v[q], v[q + h]);
+        }
+        T x = v[0];
+#pragma unroll
+        for (uint32_t s = 16; s >= 1; s /= 2) x = add_rn(x, __shfl_down_sync(0xffffffffu, x, s));
+        return __shfl_sync(0xffffffffu, x, 0);
+    } else {
+        T v[CNT];
+#pragma unroll
+        for (uint32_t q = 0; q < CNT; ++q) v[q] = part[q];
+        return glass_tree<T, CNT>(v);
+    }
+}
+
+template <typename T, uint32_t n, uint32_t N, uint32_t C>
+struct ClusterPcg2 {
+    static_assert(N % C == 0 && N >= 2 && n <= 32 && C <= 16, "unsupported shape");
+    static constexpr uint32_t G = n <= 16 ? 16 : 32;   // lanes per knot row
+    static constexpr uint32_t R = N / C;
+    static constexpr uint32_t W = 3 * n;
+    static constexpr uint32_t TILE = 3 * n * n;
+    static constexpr uint32_t NT = (R * G + 31) / 32 * 32;
+    static constexpr uint32_t XS = (n + 3) / 4 * 4;     // padded row stride of the vector windows
+    static constexpr uint32_t XLEN = (R + 2) * XS;
+    static constexpr bool TMA_OK = (TILE * sizeof(T)) % 16 == 0;
+    static constexpr size_t align16(size_t x) { return (x + 15) / 16 * 16; }
+    static constexpr size_t OFF_BAR = 0;                // 3 mbarriers: tiles, phase A, phase B
+    static constexpr size_t OFF_S = 32;
+    static constexpr size_t OFF_P = OFF_S + align16(sizeof(T) * R * TILE);
+    static constexpr size_t OFF_XP = OFF_P + align16(sizeof(T) * R * TILE);
+    static constexpr size_t OFF_XR = OFF_XP + align16(sizeof(T) * XLEN);
+    static constexpr size_t OFF_HU = OFF_XR + align16(sizeof(T) * XLEN);
+    static constexpr size_t OFF_HT = OFF_HU + align16(sizeof(T) * 2 * XS);
+    static constexpr size_t OFF_PV = OFF_HT + align16(sizeof(T) * 2 * XS);
+    static constexpr size_t OFF_PE = OFF_PV + align16(sizeof(T) * N);
+    static constexpr size_t SMEM_BYTES = OFF_PE + align16(sizeof(T) * N);
+};
+
+// band-row chain over a padded window: columns c = 0..3n-1 ascending, one FMA each
+template <typename T, uint32_t n, uint32_t XS>
+__device__ __forceinline__ T chain_padded(const T (&m)[3 * n], const T *__restrict__ xw)
+{
+    T x[3 * XS];
+    if constexpr (sizeof(T) == 4) {
+#pragma unroll
+        for (uint32_t q = 0; q < 3 * XS / 4; ++q) {
+            const float4 f = reinterpret_cast<const float4 *>(xw)[q];
+            x[4 * q] = f.x; x[4 * q + 1] = f.y; x[4 * q + 2] = f.z; x[4 * q + 3] = f.w;
+        }
+    } else {
+#pragma unroll
+        for (uint32_t q = 0; q < 3 * XS / 2; ++q) {
+            const double2 f = reinterpret_cast<const double2 *>(xw)[q];
+            x[2 * q] = f.x; x[2 * q + 1] = f.y;
+        }
+    }
+    T acc = T(0);
+#pragma unroll
+    for (uint32_t blk = 0; blk < 3; ++blk)
+#pragma unroll
+        for (uint32_t c = 0; c < n; ++c) acc = fma_rn(m[blk * n + c], x[blk * XS + c], acc);
+    return acc;
+}
+
+template <typename T, uint32_t n, uint32_t N, uint32_t C, uint32_t MINB>
+__global__ void __launch_bounds__(ClusterPcg2<T, n, N, C>::NT, MINB)
+pcg_cluster_kernel_v2(const PcgArgs<T> a)
+{
+    using K = ClusterPcg2<T, n, N, C>;
+    constexpr uint32_t R = K::R, W = K::W, TILE = K::TILE, G = K::G, XS = K::XS;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + K::OFF_BAR);
+    uint64_t *barT = bars, *barA = bars + 1, *barB = bars + 2;
+    T *sS = reinterpret_cast<T *>(smem_raw + K::OFF_S);
+    T *sP = reinterpret_cast<T *>(smem_raw + K::OFF_P);
+    T *xp = reinterpret_cast<T *>(smem_raw + K::OFF_XP);
+    T *xr = reinterpret_cast<T *>(smem_raw + K::OFF_XR);
+    T *hu = reinterpret_cast<T *>(smem_raw + K::OFF_HU);
+    T *ht = reinterpret_cast<T *>(smem_raw + K::OFF_HT);
+    T *part_v = reinterpret_cast<T *>(smem_raw + K::OFF_PV);
+    T *part_e = reinterpret_cast<T *>(smem_raw + K::OFF_PE);
+
+    const uint32_t t = threadIdx.x;
+    const uint32_t j = t % G;                      // lane inside the knot-row group
+    const uint32_t g = t / G;
+    const bool group_live = g < R;
+    const uint32_t k = group_live ? g : R - 1;     // local knot row (clamped for padding lanes)
+    const bool is_row = group_live && j < n;
+    const uint32_t cr = cluster_ctarank();
+    const uint32_t cid = cluster_idx(), ncl = cluster_count();
+    const uint32_t b = cr * R + k;
+    const bool has_left = cr > 0, has_right = cr + 1 < C;
+    const uint32_t left = has_left ? cr - 1 : cr, right = has_right ? cr + 1 : cr;
+    const bool push_left = is_row && k == 0 && has_left;        // my first knot row -> left neighbour's right halo
+    const bool push_right = is_row && k == R - 1 && has_right;  // my last knot row  -> right neighbour's left halo
+    const bool fan = group_live && j < C;                       // lane j of a group sends the partial to CTA j
+    const bool own_lhalo = group_live && g == 0 && j < n, own_rhalo = group_live && g == R - 1 && j < n;
+
+    const uint32_t jn = j < n ? j : 0;
+    const uint32_t rem_hu_l = map_to_cta(smem_u32(hu + XS + jn), left), rem_hu_r = map_to_cta(smem_u32(hu + jn), right);
+    const uint32_t rem_ht_l = map_to_cta(smem_u32(ht + XS + jn), left), rem_ht_r = map_to_cta(smem_u32(ht + jn), right);
+    const uint32_t rem_xr_l = map_to_cta(smem_u32(xr + (R + 1) * XS + jn), left), rem_xr_r = map_to_cta(smem_u32(xr + jn), right);
+    const uint32_t rem_A_l = map_to_cta(smem_u32(barA), left), rem_A_r = map_to_cta(smem_u32(barA), right);
+    const uint32_t rem_B_l = map_to_cta(smem_u32(barB), left), rem_B_r = map_to_cta(smem_u32(barB), right);
+    const uint32_t fan_to = j < C ? j : 0;
+    const uint32_t rem_pv = map_to_cta(smem_u32(part_v + part_index<N>(b)), fan_to);
+    const uint32_t rem_pe = map_to_cta(smem_u32(part_e + part_index<N>(b)), fan_to);
+    const uint32_t rem_A_f = map_to_cta(smem_u32(barA), fan_to), rem_B_f = map_to_cta(smem_u32(barB), fan_to);
+
+    const uint32_t halo_bytes = ((has_left ? 1u : 0u) + (has_right ? 1u : 0u)) * n * (uint32_t)sizeof(T);
+    const uint32_t full_bytes = N * (uint32_t)sizeof(T) + halo_bytes;
+
+    if (t == 0) {
+        mbar_init(barT, 1);
+        mbar_init(barA, 1);
+        mbar_init(barB, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    cluster_sync();   // all CTAs resident, all mbarriers initialised, before any DSMEM traffic
+
+    uint32_t phT = 0, phA = 0, phB = 0;
+    for (uint32_t sys = cid; sys < a.batch; sys += ncl) {
+        const size_t moff = ((size_t)sys * N + (size_t)cr * R) * TILE;
+        const size_t vbase = (size_t)sys * N * n;
+        const T *gS = a.S + moff, *gP = a.Pinv + moff;
+        const bool tma = K::TMA_OK && a.use_tma;
+
+        if (tma) {
+            if (t == 0) {
+                fence_proxy_async();
+                constexpr uint32_t total = (uint32_t)(sizeof(T) * R * TILE);
+                constexpr uint32_t CH = 16384;
+                mbar_arrive_expect_tx(barT, 2 * total);
+                for (uint32_t o = 0; o < total; o += CH) {
+                    const uint32_t len = total - o < CH ? total - o : CH;
+                    tma_bulk_g2s(reinterpret_cast<unsigned char *>(sS) + o, reinterpret_cast<const unsigned char *>(gS) + o, len, barT);
+                    tma_bulk_g2s(reinterpret_cast<unsigned char *>(sP) + o, reinterpret_cast<const unsigned char *>(gP) + o, len, barT);
+                }
+            }
+        } else {
+            for (uint32_t i = t; i < R * TILE; i += K::NT) { sS[i] = gS[i]; sP[i] = gP[i]; }
+        }
+        if (t == 0) mbar_arrive_expect_tx(barA, halo_bytes);        // prologue exchange: r boundary rows only
+        // lambda window: own knot rows plus one each side (absent neighbours read as zero)
+        for (uint32_t i = t; i < (R + 2) * n; i += K::NT) {
+            const uint32_t row = i / n, e = i % n;
+            const long kb = (long)(cr * R) + (long)row - 1;
+            xp[row * XS + e] = (kb >= 0 && kb < (long)N) ? a.lambda[vbase + (size_t)kb * n + e] : T(0);
+        }
+        if (own_lhalo && !has_left) xr[j] = T(0);
+        if (own_rhalo && !has_right) xr[(R + 1) * XS + j] = T(0);
+        T lam = T(0), gam = T(0);
+        if (is_row) {
+            lam = a.lambda[vbase + (size_t)b * n + j];
+            gam = a.gamma[vbase + (size_t)b * n + j];
+        }
+        if (tma) mbar_wait(barT, phT);
+        phT ^= 1u;
+        __syncthreads();
+        if (cr == 0)
+            for (uint32_t i = t; i < n * n; i += K::NT) { sS[i] = T(0); sP[i] = T(0); }
+        if (cr == C - 1)
+            for (uint32_t i = t; i < n * n; i += K::NT) { sS[(R - 1) * TILE + 2 * n * n + i] = T(0); sP[(R - 1) * TILE + 2 * n * n + i] = T(0); }
+        __syncthreads();
+
+        // this thread's rows of S and Pinv live in registers for the whole solve
+        T ms[W], mp[W];
+        {
+            const T *rowS = sS + k * TILE + jn, *rowP = sP + k * TILE + jn;
+#pragma unroll
+            for (uint32_t c = 0; c < W; ++c) {
+                ms[c] = is_row ? rowS[c * n] : T(0);
+                mp[c] = is_row ? rowP[c * n] : T(0);
+            }
+        }
+        const T *wp = xp + k * XS, *wr = xr + k * XS;      // 3-row windows [k-1 | k | k+1]
+        T *own_p = xp + (k + 1) * XS + jn, *own_r = xr + (k + 1) * XS + jn;
+
+        // ---- r = gamma - S*lambda ; exchange boundary rows of r            (pcg.cuh:118-126)
+        T r = gam - chain_padded<T, n, XS>(ms, wp);
+        if (is_row) *own_r = r;
+        if (push_left) st_async(rem_xr_l, r, rem_A_l);
+        if (push_right) st_async(rem_xr_r, r, rem_A_r);
+        if (t == 0) mbar_arrive_expect_tx(barB, full_bytes);
+        mbar_wait(barA, phA);
+        phA ^= 1u;
+        __syncthreads();
+        // ---- r~ = Pinv*r ; p = r~ ; eta = r.r~                             (pcg.cuh:130-149)
+        T rt = chain_padded<T, n, XS>(mp, wr);
+        {
+            T x = glass_tree_shfl<T, n, G>(mul_rn(r, rt), j);
+            x = __shfl_sync(0xffffffffu, x, 0, G);
+            if (fan) st_async(rem_pe, x, rem_B_f);
+        }
+        if (push_left) st_async(rem_ht_l, rt, rem_B_l);
+        if (push_right) st_async(rem_ht_r, rt, rem_B_r);
+        mbar_wait(barB, phB);
+        phB ^= 1u;
+        T eta = glass_tree_part<T, N>(part_e);
+        T p = rt, ups = T(0);
+        if (is_row) *own_p = p;
+        if (own_lhalo) xp[j] = has_left ? ht[j] : T(0);
+        if (own_rhalo) xp[(R + 1) * XS + j] = has_right ? ht[XS + j] : T(0);
+
+        uint32_t iter = 0;
+        uint8_t max_iter_exit = 1;
+        for (; iter < a.max_iter; ++iter) {
+            if (t == 0) mbar_arrive_expect_tx(barA, full_bytes);
+            __syncthreads();
+            // ---- upsilon = S*p ; v = p.upsilon                             (pcg.cuh:156-167)
+            ups = chain_padded<T, n, XS>(ms, wp);
+            {
+                T x = glass_tree_shfl<T, n, G>(mul_rn(p, ups), j);
+                x = __shfl_sync(0xffffffffu, x, 0, G);
+                if (fan) st_async(rem_pv, x, rem_A_f);
+            }
+            if (push_left) st_async(rem_hu_l, ups, rem_A_l);
+            if (push_right) st_async(rem_hu_r, ups, rem_A_r);
+            mbar_wait(barA, phA);
+            phA ^= 1u;
+            const T alpha = eta / glass_tree_part<T, N>(part_v);               // :169
+            // ---- lambda += alpha p ; r -= alpha upsilon (own rows + halo copies)   (:172-176)
+            lam = fma_rn(alpha, p, lam);
+            r = fma_rn(-alpha, ups, r);
+            if (is_row) *own_r = r;
+            if (own_lhalo && has_left) xr[j] = fma_rn(-alpha, hu[j], xr[j]);
+            if (own_rhalo && has_right) xr[(R + 1) * XS + j] = fma_rn(-alpha, hu[XS + j], xr[(R + 1) * XS + j]);
+            if (t == 0) mbar_arrive_expect_tx(barB, full_bytes);
+            __syncthreads();
+            // ---- r~ = Pinv*r ; eta' = r.r~                                 (:180-193)
+            rt = chain_padded<T, n, XS>(mp, wr);
+            {
+                T x = glass_tree_shfl<T, n, G>(mul_rn(r, rt), j);
+                x = __shfl_sync(0xffffffffu, x, 0, G);
+                if (fan) st_async(rem_pe, x, rem_B_f);
+            }
+            if (push_left) st_async(rem_ht_l, rt, rem_B_l);
+            if (push_right) st_async(rem_ht_r, rt, rem_B_r);
+            mbar_wait(barB, phB);
+            phB ^= 1u;
+            const T eta_new = glass_tree_part<T, N>(part_e);
+            if (abs_(eta_new) < a.exit_tol) { ++iter; max_iter_exit = 0; break; }   // :195
+            const T beta = eta_new / eta;                                       // :199-200
+            eta = eta_new;
+            // ---- p = r~ + beta p (own rows + halo copies)                   (:203-206)
+            p = fma_rn(beta, p, rt);
+            if (is_row) *own_p = p;
+            if (own_lhalo && has_left) xp[j] = fma_rn(beta, xp[j], ht[j]);
+            if (own_rhalo && has_right) xp[(R + 1) * XS + j] = fma_rn(beta, xp[(R + 1) * XS + j], ht[XS + j]);
+        }
+
+        // ---- outputs                                                        (:212-215)
+        if (is_row) {
+            const size_t o = vbase + (size_t)b * n + j;
+            a.lambda[o] = lam;
+            if (a.r_out) a.r_out[o] = r;
+            if (a.p_out) a.p_out[o] = p;
+        }
+        if (cr == 0 && t == 0) {
+            a.iters[sys] = iter;
+            a.max_iter_exit[sys] = max_iter_exit;
+        }
+        __syncthreads();
+    }
+    cluster_sync();
+}
+
+}  // namespace gbd

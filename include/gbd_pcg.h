@@ -47,12 +47,14 @@ int gbd_pcg_last_cuda_error(void); /* cudaError_t of the last failing CUDA call 
  * interface.cuh:110); here the pairs are enumerated at run time. */
 int gbd_pcg_supported(uint32_t n, uint32_t N, int is_f64);
 int gbd_pcg_num_variants(void);
-int gbd_pcg_variant_at(int i, uint32_t *n, uint32_t *N, uint32_t *cluster, int *regs, int *is_f64,
+int gbd_pcg_variant_at(int i, uint32_t *n, uint32_t *N, uint32_t *cluster, int *mode, int *is_f64,
                        uint32_t *threads, size_t *smem_bytes);
 
-/* Tuning knob: pick the cluster size (CTAs per system) / tile residency used for (n, N).
- * cluster = 0 and regs = -1 restore the built-in default. */
-int gbd_pcg_set_tuning(uint32_t n, uint32_t N, int is_f64, uint32_t cluster, int regs);
+/* Tuning knob: pick the cluster size (CTAs per system) and kernel build used for (n, N).
+ * mode: 0 = v1 kernel, tiles in shared memory; 1 = v1, tiles in registers; 2 = v2 kernel (st.async +
+ * mbarrier signalling), 1 CTA/SM register budget; 3 = v2, 2 CTAs/SM budget (default for batches).
+ * cluster = 0 and mode = -1 restore the built-in default.  All modes give bit-identical results. */
+int gbd_pcg_set_tuning(uint32_t n, uint32_t N, int is_f64, uint32_t cluster, int mode);
 
 /*
  * One solve, device pointers, asynchronous on `stream` (a cudaStream_t, or NULL).

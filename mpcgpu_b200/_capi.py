@@ -87,6 +87,6 @@ def variants():
         regs, f64, smem = C.c_int(), C.c_int(), C.c_size_t()
         check(L.gbd_pcg_variant_at(i, C.byref(n), C.byref(N), C.byref(c), C.byref(regs), C.byref(f64), C.byref(t),
                                    C.byref(smem)), "gbd_pcg_variant_at")
-        out.append(dict(n=n.value, N=N.value, cluster=c.value, regs=bool(regs.value), f64=bool(f64.value),
+        out.append(dict(n=n.value, N=N.value, cluster=c.value, mode=regs.value, f64=bool(f64.value),
                         threads=t.value, smem=smem.value))
     return out

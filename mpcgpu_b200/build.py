@@ -7,7 +7,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = [os.path.join(HERE, "csrc", "gbd_capi.cu")]
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("gbd_device.cuh", "gbd_cluster_pcg.cuh")] + [
+DEPS = [os.path.join(ROOT, "include", "gbd", f) for f in os.listdir(os.path.join(ROOT, "include", "gbd"))] + [
     os.path.join(ROOT, "include", "gbd_pcg.h")]
 LIB = os.path.join(HERE, "lib", "libgbdpcg.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -11,15 +11,18 @@
 #include <vector>
 
 #include "../../include/gbd_pcg.h"
-#include "gbd_cluster_pcg.cuh"
+#include "../../include/gbd/gbd_cluster_pcg_v2.cuh"
 
 namespace {
 
 using namespace gbd;
 
+// mode: 0 = v1 kernel, tiles in shared memory; 1 = v1 kernel, tiles in registers;
+//       2 = v2 kernel (st.async/mbarrier signalling), 1 CTA/SM register budget; 3 = v2, 2 CTAs/SM budget
 struct Variant {
     uint32_t n, N, C;
-    bool regs, f64;
+    int mode;
+    bool f64;
     uint32_t nt;
     size_t smem;
     const void *kernel;
@@ -30,8 +33,16 @@ template <typename T, uint32_t n, uint32_t N, uint32_t C, bool REGS>
 Variant make_variant()
 {
     using K = ClusterPcg<T, n, N, C, REGS>;
-    return Variant{n, N, C, REGS, sizeof(T) == 8, K::NT, K::SMEM_BYTES,
+    return Variant{n, N, C, REGS ? 1 : 0, sizeof(T) == 8, K::NT, K::SMEM_BYTES,
                    (const void *)pcg_cluster_kernel<T, n, N, C, REGS>, false};
+}
+
+template <typename T, uint32_t n, uint32_t N, uint32_t C, uint32_t MINB>
+Variant make_v2()
+{
+    using K = ClusterPcg2<T, n, N, C>;
+    return Variant{n, N, C, MINB == 1 ? 2 : 3, sizeof(T) == 8, K::NT, K::SMEM_BYTES,
+                   (const void *)pcg_cluster_kernel_v2<T, n, N, C, MINB>, false};
 }
 
 // (n, N) pairs: IIWA (n=14) at the reference's horizons (include/common/settings.cuh:123-138) plus
@@ -40,6 +51,16 @@ Variant make_variant()
 std::vector<Variant> &variants()
 {
     static std::vector<Variant> v = {
+        make_v2<float, 14, 128, 8, 1>(),          make_v2<float, 14, 128, 8, 2>(),
+        make_v2<float, 14, 128, 16, 1>(),         make_v2<float, 14, 128, 4, 1>(),
+        make_v2<float, 14, 32, 4, 1>(),           make_v2<float, 14, 32, 8, 1>(),
+        make_v2<float, 14, 32, 2, 1>(),           make_v2<float, 14, 32, 4, 2>(),
+        make_v2<float, 14, 64, 8, 1>(),           make_v2<float, 14, 64, 4, 1>(),
+        make_v2<float, 14, 256, 16, 1>(),         make_v2<float, 14, 256, 8, 1>(),
+        make_v2<float, 14, 512, 16, 1>(),
+        make_v2<float, 14, 16, 4, 1>(),           make_v2<float, 14, 8, 8, 1>(),
+        make_v2<float, 6, 12, 4, 1>(),            make_v2<float, 6, 12, 1, 2>(),
+        make_v2<float, 2, 3, 1, 1>(),             make_v2<float, 2, 3, 3, 1>(),
         make_variant<float, 14, 128, 8, true>(),  make_variant<float, 14, 128, 16, true>(),
         make_variant<float, 14, 128, 4, true>(),  make_variant<float, 14, 128, 8, false>(),
         make_variant<float, 14, 32, 4, true>(),   make_variant<float, 14, 32, 8, true>(),
@@ -59,7 +80,7 @@ std::vector<Variant> &variants()
     return v;
 }
 
-struct Tuning { uint32_t n, N; bool f64; uint32_t C; int regs; };
+struct Tuning { uint32_t n, N; bool f64; uint32_t C; int mode; };
 std::vector<Tuning> &tunings() { static std::vector<Tuning> t; return t; }
 std::mutex g_mu;
 std::atomic<uint64_t> g_launches{0};
@@ -74,17 +95,19 @@ int cuda_fail(cudaError_t e)
 }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(e_); } while (0)
 
-Variant *find_variant(uint32_t n, uint32_t N, bool f64)
+Variant *find_variant(uint32_t n, uint32_t N, bool f64, bool batched)
 {
-    uint32_t wantC = 0; int wantRegs = -1;
-    for (auto &t : tunings()) if (t.n == n && t.N == N && t.f64 == f64) { wantC = t.C; wantRegs = t.regs; }
-    Variant *first = nullptr;
+    uint32_t wantC = 0; int wantMode = -1;
+    for (auto &t : tunings()) if (t.n == n && t.N == N && t.f64 == f64) { wantC = t.C; wantMode = t.mode; }
+    Variant *first = nullptr, *first_b = nullptr;
     for (auto &v : variants()) {
         if (v.n != n || v.N != N || v.f64 != f64) continue;
         if (!first) first = &v;
-        if ((wantC == 0 || v.C == wantC) && (wantRegs < 0 || (int)v.regs == wantRegs)) return &v;
+        if (!first_b && v.mode == 3) first_b = &v;      // 2-CTA/SM build: the default for batched launches
+        if ((wantC || wantMode >= 0) && (wantC == 0 || v.C == wantC) && (wantMode < 0 || v.mode == wantMode)) return &v;
     }
-    return (wantC == 0 && wantRegs < 0) ? first : nullptr;
+    if (wantC || wantMode >= 0) return nullptr;
+    return (batched && first_b) ? first_b : first;
 }
 
 int prepare(Variant &v)
@@ -120,7 +143,7 @@ int launch(uint32_t n, uint32_t N, uint32_t batch, const T *S, const T *P, const
            uint32_t *iters, uint8_t *flag, uint32_t max_iter, T tol, cudaStream_t st)
 {
     if (!S || !P || !g || !lam || !iters || !flag || batch == 0 || N < 2 || n == 0) return GBD_PCG_ERR_BADARG;
-    Variant *v = find_variant(n, N, sizeof(T) == 8);
+    Variant *v = find_variant(n, N, sizeof(T) == 8, batch > 1);
     if (!v) return GBD_PCG_ERR_UNSUPPORTED;
     int rc = prepare(*v);
     if (rc) return rc;
@@ -203,7 +226,7 @@ int gbd_pcg_variant_at(int i, uint32_t *n, uint32_t *N, uint32_t *cluster, int *
     if (n) *n = v.n;
     if (N) *N = v.N;
     if (cluster) *cluster = v.C;
-    if (regs) *regs = v.regs;
+    if (regs) *regs = v.mode;
     if (is_f64) *is_f64 = v.f64;
     if (threads) *threads = v.nt;
     if (smem_bytes) *smem_bytes = v.smem;
@@ -219,7 +242,7 @@ int gbd_pcg_set_tuning(uint32_t n, uint32_t N, int is_f64, uint32_t cluster, int
     if (cluster == 0 && regs < 0) return GBD_PCG_OK;
     bool ok = false;
     for (auto &v : variants())
-        if (v.n == n && v.N == N && v.f64 == (is_f64 != 0) && (cluster == 0 || v.C == cluster) && (regs < 0 || (int)v.regs == regs)) ok = true;
+        if (v.n == n && v.N == N && v.f64 == (is_f64 != 0) && (cluster == 0 || v.C == cluster) && (regs < 0 || v.mode == regs)) ok = true;
     if (!ok) return GBD_PCG_ERR_UNSUPPORTED;
     t.push_back(Tuning{n, N, is_f64 != 0, cluster, regs});
     return GBD_PCG_OK;

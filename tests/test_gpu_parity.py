@@ -66,7 +66,7 @@ def test_every_variant_bit_exact_vs_oracle(torch_cuda, capi, oracle_pcg):
                     for i in range(2)]
             cache[key] = (d, cap, tol, want)
         d, cap, tol, want = cache[key]
-        assert L.gbd_pcg_set_tuning(n, N, int(f64), v["cluster"], int(v["regs"])) == 0
+        assert L.gbd_pcg_set_tuning(n, N, int(f64), v["cluster"], v["mode"]) == 0
         try:
             for i in range(2):
                 got = _gpu_solve(torch_cuda, m, d, i, cap, tol, dt)
@@ -123,7 +123,7 @@ def test_batched_equals_single_and_oracle(torch_cuda, capi, oracle_pcg):
     """More systems than co-resident clusters: exercises the persistent loop and smem reuse."""
     import mpcgpu_b200 as m
     torch = torch_cuda
-    n, N, B, cap, tol = 14, 32, 300, 60, 1e-5
+    n, N, B, cap, tol = 14, 32, 300, 173, 1e-4
     d = synth.make_systems(n, N, batch=B, seed=33, nan_pads=True)
     S, P, g, lam = (_dev(torch, d[k]) for k in ("S", "Pinv", "gamma", "lambda0"))
     it = torch.zeros(B, dtype=torch.int32, device="cuda")

@@ -59,11 +59,11 @@ def main():
 
             t_zero = time_fn(zero_only, 200)
             for v in [v for v in _capi.variants() if v["n"] == n and v["N"] == N and not v["f64"]]:
-                assert L.gbd_pcg_set_tuning(n, N, 0, v["cluster"], int(v["regs"])) == 0
+                assert L.gbd_pcg_set_tuning(n, N, 0, v["cluster"], v["mode"]) == 0
                 us = time_fn(ours, 200) - t_zero
                 torch.cuda.synchronize()
                 mean_it = float(it.float().mean().item())
-                out.append(dict(impl="ours", n=n, N=N, tol=tol, cap=cap, cluster=v["cluster"], regs=v["regs"],
+                out.append(dict(impl="ours", n=n, N=N, tol=tol, cap=cap, cluster=v["cluster"], mode=v["mode"],
                                 kernel_us=us, mean_iters=mean_it, us_per_iter=us / mean_it))
                 print(out[-1], flush=True)
                 L.gbd_pcg_set_tuning(n, N, 0, 0, -1)
