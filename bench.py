@@ -362,13 +362,14 @@ def run_ours(args):
         blam = torch.zeros(Kb + Wb, Bl, n * N, device=dev)
         bit = torch.zeros(Kb + Wb, Bl, dtype=torch.int32, device=dev)
         bfl = torch.zeros(Kb + Wb, Bl, dtype=torch.uint8, device=dev)
-        gathered = torch.zeros(world * Bl, dtype=torch.uint8, device=dev)
+        from mpcgpu_b200.sharding import ShardedBatch
+        shard = ShardedBatch(n, N, BATCH_TOTAL, world, rank, dev)
+        assert shard.local == Bl
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if Bl * 2 * 3 * n * n * N * esz < (160 << 20) else None
 
         def bstep(s):
-            m.solve_batched(n, N, Bl, bS, bP, bg, blam[s], bit[s], bfl[s], MAX_ITER, EXIT_TOL)
-            if world > 1:
-                dist.all_gather_into_tensor(gathered, bfl[s])   # the one collective per outer SQP step
+            shard.iters, shard.flags = bit[s], bfl[s]
+            return shard.solve_step(bS, bP, bg, blam[s], MAX_ITER, EXIT_TOL)   # 1 launch + 1 all-gather of flags
 
         for s in range(Wb):
             bstep(s)

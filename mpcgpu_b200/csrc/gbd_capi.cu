@@ -140,7 +140,7 @@ int max_clusters(Variant &v, int *out)
 
 template <typename T>
 int launch(uint32_t n, uint32_t N, uint32_t batch, const T *S, const T *P, const T *g, T *lam, T *r, T *p,
-           uint32_t *iters, uint8_t *flag, uint32_t max_iter, T tol, cudaStream_t st)
+           uint32_t *iters, uint8_t *flag, uint32_t max_iter, T tol, cudaStream_t st, bool no_tma = false)
 {
     if (!S || !P || !g || !lam || !iters || !flag || batch == 0 || N < 2 || n == 0) return GBD_PCG_ERR_BADARG;
     Variant *v = find_variant(n, N, sizeof(T) == 8, batch > 1);
@@ -163,7 +163,7 @@ int launch(uint32_t n, uint32_t N, uint32_t batch, const T *S, const T *P, const
     PcgArgs<T> a;
     a.S = S; a.Pinv = P; a.gamma = g; a.lambda = lam; a.r_out = r; a.p_out = p;
     a.iters = iters; a.max_iter_exit = flag; a.batch = batch; a.max_iter = max_iter; a.exit_tol = tol;
-    a.use_tma = (((uintptr_t)S | (uintptr_t)P) & 15u) == 0 ? 1u : 0u;
+    a.use_tma = (!no_tma && (((uintptr_t)S | (uintptr_t)P) & 15u) == 0) ? 1u : 0u;
 
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute at[1];
@@ -189,6 +189,8 @@ struct gbd_pcg_plan {
     void *dS, *dP, *dg, *dl;
     uint32_t *d_iters;
     uint8_t *d_flag;
+    uint32_t *h_iters_pin;   // pinned + mapped result slots for the zero-copy path
+    uint8_t *h_flag_pin;
     cudaStream_t st;
 };
 
@@ -304,7 +306,9 @@ int gbd_pcg_plan_create(uint32_t n, uint32_t N, uint32_t batch, int is_f64, gbd_
         (e = cudaMalloc(&p->dS, mat)) != cudaSuccess || (e = cudaMalloc(&p->dP, mat)) != cudaSuccess ||
         (e = cudaMalloc(&p->dg, vec)) != cudaSuccess || (e = cudaMalloc(&p->dl, vec)) != cudaSuccess ||
         (e = cudaMalloc((void **)&p->d_iters, sizeof(uint32_t) * batch)) != cudaSuccess ||
-        (e = cudaMalloc((void **)&p->d_flag, batch)) != cudaSuccess) {
+        (e = cudaMalloc((void **)&p->d_flag, batch)) != cudaSuccess ||
+        (e = cudaHostAlloc((void **)&p->h_iters_pin, sizeof(uint32_t) * batch, cudaHostAllocMapped)) != cudaSuccess ||
+        (e = cudaHostAlloc((void **)&p->h_flag_pin, batch, cudaHostAllocMapped)) != cudaSuccess) {
         gbd_pcg_plan_destroy(p);
         return cuda_fail(e);
     }
@@ -316,6 +320,8 @@ int gbd_pcg_plan_destroy(gbd_pcg_plan *p)
 {
     if (!p) return GBD_PCG_OK;
     cudaFree(p->dS); cudaFree(p->dP); cudaFree(p->dg); cudaFree(p->dl); cudaFree(p->d_iters); cudaFree(p->d_flag);
+    if (p->h_iters_pin) cudaFreeHost(p->h_iters_pin);
+    if (p->h_flag_pin) cudaFreeHost(p->h_flag_pin);
     if (p->st) cudaStreamDestroy(p->st);
     free(p);
     return GBD_PCG_OK;
@@ -324,12 +330,45 @@ int gbd_pcg_plan_destroy(gbd_pcg_plan *p)
 }  // extern "C"
 
 namespace {
+// device alias of a pinned / registered host pointer, or nullptr for pageable memory
+const void *device_alias(const void *h)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, h) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+}
+
+// GBD_PCG_ZEROCOPY: 1 (default) = pinned host buffers are read/written by the kernel itself over PCIe
+// (TMA bulk loads straight from host memory, lambda written straight back), 2 = same with plain
+// loads instead of TMA, 0 = always stage through device buffers with cudaMemcpyAsync.
+int zerocopy_mode()
+{
+    static int mode = [] { const char *e = getenv("GBD_PCG_ZEROCOPY"); return e ? atoi(e) : 1; }();
+    return mode;
+}
+
 template <typename T>
 int plan_solve_host(gbd_pcg_plan *p, const T *hS, const T *hP, const T *hg, T *hl, uint32_t max_iter, T tol,
                     uint32_t *h_iters, uint8_t *h_flag)
 {
     if (!p || !hS || !hP || !hg || !hl || !h_iters || !h_flag) return GBD_PCG_ERR_BADARG;
     if (p->f64 != (sizeof(T) == 8)) return GBD_PCG_ERR_BADARG;
+    if (zerocopy_mode() != 0) {
+        const T *zS = (const T *)device_alias(hS), *zP = (const T *)device_alias(hP), *zg = (const T *)device_alias(hg);
+        T *zl = (T *)device_alias(hl);
+        if (zS && zP && zg && zl) {
+            uint32_t *zi = nullptr; uint8_t *zf = nullptr;
+            CK(cudaHostGetDevicePointer((void **)&zi, p->h_iters_pin, 0));
+            CK(cudaHostGetDevicePointer((void **)&zf, p->h_flag_pin, 0));
+            int rc = launch<T>(p->n, p->N, p->batch, zS, zP, zg, zl, (T *)nullptr, (T *)nullptr, zi, zf, max_iter, tol, p->st,
+                               zerocopy_mode() == 2);
+            if (rc) return rc;
+            CK(cudaStreamSynchronize(p->st));
+            memcpy(h_iters, p->h_iters_pin, sizeof(uint32_t) * p->batch);
+            memcpy(h_flag, p->h_flag_pin, p->batch);
+            return GBD_PCG_OK;
+        }
+    }
     const size_t mat = (size_t)3 * p->n * p->n * p->N * p->batch * sizeof(T), vec = (size_t)p->n * p->N * p->batch * sizeof(T);
     CK(cudaMemcpyAsync(p->dS, hS, mat, cudaMemcpyHostToDevice, p->st));
     CK(cudaMemcpyAsync(p->dP, hP, mat, cudaMemcpyHostToDevice, p->st));

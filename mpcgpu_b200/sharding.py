@@ -1,0 +1,67 @@
+"""Multi-GPU batching: independent systems are sharded by contiguous blocks, one process per GPU.
+
+The single-trajectory solve does not shard (2 global reductions + 2 halo exchanges per iteration over
+a <= 25 MB problem: a cross-GPU hop per step would dominate) -- "replicas only".  A BATCH of systems
+does: system i lives on rank ``i // ceil(batch / world)``; a solve needs no communication, and the one
+collective per outer SQP step is an all-gather of the per-system converged flags (<= 1 byte each),
+which is what the caller's SQP loop needs to decide which trajectories take another step.
+Works with any torch.distributed backend (NCCL on GPUs, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+
+def shard_range(batch: int, world: int, rank: int) -> tuple[int, int]:
+    """Contiguous block [lo, hi) of systems owned by `rank` (last ranks may own fewer or none)."""
+    if batch < 0 or world < 1 or not 0 <= rank < world:
+        raise ValueError("bad shard arguments")
+    per = -(-batch // world)
+    lo = min(batch, rank * per)
+    return lo, min(batch, lo + per)
+
+
+def owner_of(system: int, batch: int, world: int) -> int:
+    per = -(-batch // world)
+    return system // per
+
+
+def gather_converged(local_not_converged, batch: int, world: int, rank: int, group=None):
+    """All-gather the per-system `max_iter_exit` bytes of every shard into one [batch] uint8 tensor
+    (same device as the input).  One collective, `ceil(batch/world)` bytes per rank."""
+    import torch
+    import torch.distributed as dist
+
+    per = -(-batch // world)
+    lo, hi = shard_range(batch, world, rank)
+    if local_not_converged.numel() != hi - lo or local_not_converged.dtype != torch.uint8:
+        raise ValueError("expected this rank's uint8 flags")
+    send = local_not_converged
+    if hi - lo != per:                                   # ragged tail: pad to the common block size
+        send = torch.zeros(per, dtype=torch.uint8, device=local_not_converged.device)
+        send[: hi - lo] = local_not_converged
+    if world == 1:
+        return send[:batch].clone()
+    out = torch.empty(world * per, dtype=torch.uint8, device=send.device)
+    dist.all_gather_into_tensor(out, send.contiguous(), group=group)
+    return out[:batch]
+
+
+class ShardedBatch:
+    """This rank's shard of a batch of systems, resident on its GPU, plus the per-step collective."""
+
+    def __init__(self, n: int, N: int, batch: int, world: int, rank: int, device):
+        import torch
+        self.n, self.N, self.batch, self.world, self.rank = n, N, batch, world, rank
+        self.lo, self.hi = shard_range(batch, world, rank)
+        self.local = self.hi - self.lo
+        self.device = device
+        self.iters = torch.zeros(max(1, self.local), dtype=torch.int32, device=device)
+        self.flags = torch.zeros(max(1, self.local), dtype=torch.uint8, device=device)
+
+    def solve_step(self, d_S, d_Pinv, d_gamma, d_lambda, max_iter: int, exit_tol: float):
+        """Solve the local shard (one launch) and all-gather the converged flags (one collective).
+        Returns the [batch] uint8 `max_iter_exit` vector of the whole batch."""
+        from . import solver
+        if self.local:
+            solver.solve_batched(self.n, self.N, self.local, d_S, d_Pinv, d_gamma, d_lambda, self.iters, self.flags,
+                                 max_iter, exit_tol)
+        return gather_converged(self.flags[: self.local], self.batch, self.world, self.rank)

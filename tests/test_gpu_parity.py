@@ -183,6 +183,14 @@ def test_host_buffer_plan_and_linsys_window(torch_cuda, capi, oracle_pcg):
     for i in range(3):
         assert its[i] == want[i]["iters"] and np.array_equal(lamb[i], want[i]["lam"])
     plan.close()
+    # pinned host buffers: the zero-copy path (kernel reads/writes host memory itself)
+    pin = {k: torch.from_numpy(d[k]).pin_memory() for k in ("S", "Pinv", "gamma")}
+    lamp = torch.zeros(3, n * N).pin_memory()
+    plan = m.HostPlan(n, N, batch=3)
+    its, fls = plan.solve(pin["S"].numpy(), pin["Pinv"].numpy(), pin["gamma"].numpy(), lamp.numpy(), cap, tol)
+    for i in range(3):
+        assert its[i] == want[i]["iters"] and np.array_equal(lamp[i].numpy(), want[i]["lam"])
+    plan.close()
     # the SQP linsys window
     S, P, g = (_dev(torch, d[k][1]) for k in ("S", "Pinv", "gamma"))
     lamd = _dev(torch, d["lambda0"][1])
