@@ -11,14 +11,16 @@
 #include <vector>
 
 #include "../../include/gbd_pcg.h"
-#include "../../include/gbd/gbd_cluster_pcg_v2.cuh"
+#include "../../include/gbd/gbd_grid_pcg.cuh"
+#include <map>
 
 namespace {
 
 using namespace gbd;
 
 // mode: 0 = v1 kernel, tiles in shared memory; 1 = v1 kernel, tiles in registers;
-//       2 = v2 kernel (st.async/mbarrier signalling), 1 CTA/SM register budget; 3 = v2, 2 CTAs/SM budget
+//       2 = v2 kernel (st.async/mbarrier signalling), 1 CTA/SM register budget; 3 = v2, 2 CTAs/SM budget;
+//       4 = grid kernel (whole GPU on one system, packets through L2; C then holds the CTA count)
 struct Variant {
     uint32_t n, N, C;
     int mode;
@@ -27,6 +29,7 @@ struct Variant {
     size_t smem;
     const void *kernel;
     bool prepared;
+    size_t ws_words;   // grid kernel: u64 words of packet workspace
 };
 
 template <typename T, uint32_t n, uint32_t N, uint32_t C, bool REGS>
@@ -34,7 +37,7 @@ Variant make_variant()
 {
     using K = ClusterPcg<T, n, N, C, REGS>;
     return Variant{n, N, C, REGS ? 1 : 0, sizeof(T) == 8, K::NT, K::SMEM_BYTES,
-                   (const void *)pcg_cluster_kernel<T, n, N, C, REGS>, false};
+                   (const void *)pcg_cluster_kernel<T, n, N, C, REGS>, false, 0};
 }
 
 template <typename T, uint32_t n, uint32_t N, uint32_t C, uint32_t MINB>
@@ -42,7 +45,15 @@ Variant make_v2()
 {
     using K = ClusterPcg2<T, n, N, C>;
     return Variant{n, N, C, MINB == 1 ? 2 : 3, sizeof(T) == 8, K::NT, K::SMEM_BYTES,
-                   (const void *)pcg_cluster_kernel_v2<T, n, N, C, MINB>, false};
+                   (const void *)pcg_cluster_kernel_v2<T, n, N, C, MINB>, false, 0};
+}
+
+template <typename T, uint32_t n, uint32_t N, uint32_t R>
+Variant make_grid()
+{
+    using K = GridPcg<T, n, N, R>;
+    return Variant{n, N, K::CTAS, 4, sizeof(T) == 8, K::NT_MIN < 128 ? 128 : K::NT_MIN, K::SMEM_BYTES,
+                   (const void *)pcg_grid_kernel<T, n, N, R>, false, K::WS_WORDS};
 }
 
 // (n, N) pairs: IIWA (n=14) at the reference's horizons (include/common/settings.cuh:123-138) plus
@@ -74,6 +85,11 @@ std::vector<Variant> &variants()
         make_variant<float, 6, 12, 4, true>(),    make_variant<float, 6, 12, 1, true>(),
         make_variant<float, 6, 12, 2, false>(),
         make_variant<float, 2, 3, 1, true>(),     make_variant<float, 2, 3, 3, false>(),
+        make_grid<float, 64, 256, 2>(),
+        make_grid<float, 14, 512, 4>(),           make_grid<float, 14, 128, 1>(),
+        make_grid<float, 14, 32, 1>(),            make_grid<float, 14, 256, 2>(),
+        make_grid<float, 6, 12, 1>(),             make_grid<float, 2, 3, 1>(),
+        make_grid<double, 14, 32, 1>(),
         make_variant<double, 14, 128, 8, false>(), make_variant<double, 14, 32, 8, false>(),
         make_variant<double, 6, 12, 4, false>(),  make_variant<double, 2, 3, 1, false>(),
     };
@@ -116,7 +132,7 @@ int prepare(Variant &v)
     std::lock_guard<std::mutex> lk(g_mu);
     if (v.prepared) return GBD_PCG_OK;
     if (v.smem > 48 * 1024) CK(cudaFuncSetAttribute(v.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem));
-    if (v.C > 8) CK(cudaFuncSetAttribute(v.kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    if (v.C > 8 && v.mode != 4) CK(cudaFuncSetAttribute(v.kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     v.prepared = true;
     return GBD_PCG_OK;
 }
@@ -138,6 +154,53 @@ int max_clusters(Variant &v, int *out)
     return GBD_PCG_OK;
 }
 
+// grid kernel: one cooperative launch per system; packet workspace per (kernel, stream), zeroed once
+struct GridWs { unsigned long long *ws; uint32_t epoch; };
+std::map<std::pair<const void *, cudaStream_t>, GridWs> &grid_ws() { static std::map<std::pair<const void *, cudaStream_t>, GridWs> m; return m; }
+
+template <typename T>
+int launch_grid(Variant &v, uint32_t batch, const T *S, const T *P, const T *g, T *lam, T *r, T *p, uint32_t *iters,
+                uint8_t *flag, uint32_t max_iter, T tol, cudaStream_t st, bool no_tma)
+{
+    GridWs *w;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto key = std::make_pair(v.kernel, st);
+        auto it = grid_ws().find(key);
+        if (it == grid_ws().end()) {
+            GridWs nw{nullptr, 0};
+            CK(cudaMalloc((void **)&nw.ws, v.ws_words * sizeof(unsigned long long)));
+            CK(cudaMemsetAsync(nw.ws, 0, v.ws_words * sizeof(unsigned long long), st));
+            it = grid_ws().emplace(key, nw).first;
+        }
+        w = &it->second;
+    }
+    const size_t ms = (size_t)3 * v.n * v.n * v.N, vs = (size_t)v.n * v.N;
+    for (uint32_t i = 0; i < batch; ++i) {
+        GridArgs<T> ga;
+        ga.a.S = S + i * ms; ga.a.Pinv = P + i * ms; ga.a.gamma = g + i * vs; ga.a.lambda = lam + i * vs;
+        ga.a.r_out = r ? r + i * vs : nullptr; ga.a.p_out = p ? p + i * vs : nullptr;
+        ga.a.iters = iters + i; ga.a.max_iter_exit = flag + i; ga.a.batch = 1; ga.a.max_iter = max_iter; ga.a.exit_tol = tol;
+        ga.a.use_tma = (!no_tma && (((uintptr_t)ga.a.S | (uintptr_t)ga.a.Pinv) & 15u) == 0) ? 1u : 0u;
+        ga.ws = w->ws;
+        ga.epoch_base = w->epoch;
+        w->epoch += 2u * max_iter + 4u;                      // upper bound on the phases one launch can use
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute at[1];
+        cfg.gridDim = dim3(v.C);
+        cfg.blockDim = dim3(v.nt);
+        cfg.dynamicSmemBytes = v.smem;
+        cfg.stream = st;
+        at[0].id = cudaLaunchAttributeCooperative;           // co-residency of all CTAs (they poll each other)
+        at[0].val.cooperative = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        void *args[] = {&ga};
+        CK(cudaLaunchKernelExC(&cfg, v.kernel, args));
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    return GBD_PCG_OK;
+}
+
 template <typename T>
 int launch(uint32_t n, uint32_t N, uint32_t batch, const T *S, const T *P, const T *g, T *lam, T *r, T *p,
            uint32_t *iters, uint8_t *flag, uint32_t max_iter, T tol, cudaStream_t st, bool no_tma = false)
@@ -147,6 +210,8 @@ int launch(uint32_t n, uint32_t N, uint32_t batch, const T *S, const T *P, const
     if (!v) return GBD_PCG_ERR_UNSUPPORTED;
     int rc = prepare(*v);
     if (rc) return rc;
+
+    if (v->mode == 4) return launch_grid<T>(*v, batch, S, P, g, lam, r, p, iters, flag, max_iter, tol, st, no_tma);
 
     uint32_t nclusters = batch;
     if (batch > 1) {

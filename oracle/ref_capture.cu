@@ -1,0 +1,97 @@
+// ref_capture.cu -- dumps real IIWA Schur systems produced by the REFERENCE's own assembly kernels.
+// TEST INFRASTRUCTURE ONLY.  Compiled by oracle/Makefile against the reference headers where they lie
+// (one binary per KNOT_POINTS, like every reference build) into oracle/_ref/.
+//
+// It reproduces the first steps of sqpSolvePcg (include/pcg/sqp.cuh:94-219) on the reference trajectory
+// (examples/trajfiles/0_0_*, loaded as examples/track_iiwa_pcg.cu:84-112 does): generate_kkt_submatrices
+// then form_schur_system at rho = 1e-3, and writes (S, Pinv, gamma) of each requested system as raw
+// float32.  d_S / d_Pinv are pre-filled with 0xFF bytes (NaN) so the pad tiles the reference never
+// writes are visibly garbage.
+//   ref_capture <traj.csv> <eepos.traj> <out.bin> <knot offset> <count> <perturb 0|1>
+// count > 1 with perturb = 1 builds BASELINE config 4's batch: system i = the window at <offset> plus
+// N(0, 0.05^2) on q, N(0, 0.01^2) on qd, N(0, 1) on u, std::mt19937_64(1234 + i).
+#include <cstdio>
+#include <fstream>
+#include <iostream>
+#include <random>
+#include <sstream>
+#include <string>
+#include <vector>
+#include "mpcsim.cuh"
+#include "dynamics/rbd_plant.cuh"
+#include "settings.cuh"
+#include "utils/experiment.cuh"
+#include "gpu_pcg.cuh"
+
+int main(int argc, char **argv)
+{
+    if (argc < 7) { fprintf(stderr, "usage: ref_capture traj.csv eepos.traj out.bin offset count perturb\n"); return 2; }
+    constexpr uint32_t state_size = grid::NUM_JOINTS * 2, control_size = grid::NUM_JOINTS, knot_points = KNOT_POINTS;
+    const linsys_t timestep = .015625;
+    const uint32_t offset = atoi(argv[4]), count = atoi(argv[5]);
+    const bool perturb = atoi(argv[6]) != 0;
+    auto xu2d = readCSVToVecVec<linsys_t>(argv[1]);
+    auto ee2d = readCSVToVecVec<linsys_t>(argv[2]);
+    if (xu2d.size() < offset + knot_points || ee2d.size() < offset + knot_points) { fprintf(stderr, "trajectory too short\n"); return 3; }
+    std::vector<linsys_t> xu0, ee;
+    for (uint32_t k = 0; k < knot_points; k++) {
+        const auto &row = xu2d[offset + k];
+        const uint32_t take = (k + 1 < knot_points) ? state_size + control_size : state_size;
+        xu0.insert(xu0.end(), row.begin(), row.begin() + take);
+        ee.insert(ee.end(), ee2d[offset + k].begin(), ee2d[offset + k].begin() + 6);
+    }
+    const uint32_t traj_len = (state_size + control_size) * knot_points - control_size;
+    const uint32_t states_sq = state_size * state_size, controls_sq = control_size * control_size;
+    const size_t G_bytes = ((states_sq + controls_sq) * knot_points - controls_sq) * sizeof(linsys_t);
+    const size_t C_bytes = (states_sq + state_size * control_size) * (knot_points - 1) * sizeof(linsys_t);
+    const size_t g_bytes = ((state_size + control_size) * knot_points - control_size) * sizeof(linsys_t);
+    const size_t c_bytes = state_size * knot_points * sizeof(linsys_t);
+    const size_t mat = 3 * (size_t)states_sq * knot_points, vec = (size_t)state_size * knot_points;
+
+    linsys_t *d_G, *d_C, *d_g, *d_c, *d_S, *d_Pinv, *d_gamma, *d_xu, *d_xs, *d_ee;
+    gpuErrchk(cudaMalloc(&d_G, G_bytes)); gpuErrchk(cudaMalloc(&d_C, C_bytes));
+    gpuErrchk(cudaMalloc(&d_g, g_bytes)); gpuErrchk(cudaMalloc(&d_c, c_bytes));
+    gpuErrchk(cudaMalloc(&d_S, mat * sizeof(linsys_t))); gpuErrchk(cudaMalloc(&d_Pinv, mat * sizeof(linsys_t)));
+    gpuErrchk(cudaMalloc(&d_gamma, vec * sizeof(linsys_t)));
+    gpuErrchk(cudaMalloc(&d_xu, traj_len * sizeof(linsys_t))); gpuErrchk(cudaMalloc(&d_xs, state_size * sizeof(linsys_t)));
+    gpuErrchk(cudaMalloc(&d_ee, 6 * knot_points * sizeof(linsys_t)));
+    gpuErrchk(cudaMemcpy(d_ee, ee.data(), 6 * knot_points * sizeof(linsys_t), cudaMemcpyHostToDevice));
+    void *d_dynmem = gato_plant::initializeDynamicsConstMem<linsys_t>();
+    linsys_t rho = 1e-3;
+
+    FILE *f = fopen(argv[3], "wb");
+    std::vector<linsys_t> hS(mat), hP(mat), hg(vec);
+    for (uint32_t i = 0; i < count; i++) {
+        std::vector<linsys_t> xu = xu0;
+        if (perturb) {
+            std::mt19937_64 gen(1234 + i);
+            std::normal_distribution<double> nq(0.0, 0.05), nqd(0.0, 0.01), nu(0.0, 1.0);
+            for (uint32_t k = 0; k < knot_points; k++) {
+                linsys_t *row = xu.data() + (size_t)k * (state_size + control_size);
+                for (uint32_t e = 0; e < control_size; e++) row[e] += (linsys_t)nq(gen);
+                for (uint32_t e = control_size; e < state_size; e++) row[e] += (linsys_t)nqd(gen);
+                if (k + 1 < knot_points)
+                    for (uint32_t e = 0; e < control_size; e++) row[state_size + e] += (linsys_t)nu(gen);
+            }
+        }
+        gpuErrchk(cudaMemcpy(d_xu, xu.data(), traj_len * sizeof(linsys_t), cudaMemcpyHostToDevice));
+        gpuErrchk(cudaMemcpy(d_xs, xu.data(), state_size * sizeof(linsys_t), cudaMemcpyHostToDevice));
+        gpuErrchk(cudaMemset(d_S, 0xFF, mat * sizeof(linsys_t)));
+        gpuErrchk(cudaMemset(d_Pinv, 0xFF, mat * sizeof(linsys_t)));
+        generate_kkt_submatrices<linsys_t><<<knot_points, KKT_THREADS, 2 * get_kkt_smem_size<linsys_t>(state_size, control_size)>>>(
+            state_size, control_size, knot_points, d_G, d_C, d_g, d_c, d_dynmem, timestep, d_ee, d_xs, d_xu);
+        gpuErrchk(cudaPeekAtLastError());
+        form_schur_system<linsys_t>(state_size, control_size, knot_points, d_G, d_C, d_g, d_c, d_S, d_Pinv, d_gamma, rho);
+        gpuErrchk(cudaPeekAtLastError());
+        gpuErrchk(cudaDeviceSynchronize());
+        gpuErrchk(cudaMemcpy(hS.data(), d_S, mat * sizeof(linsys_t), cudaMemcpyDeviceToHost));
+        gpuErrchk(cudaMemcpy(hP.data(), d_Pinv, mat * sizeof(linsys_t), cudaMemcpyDeviceToHost));
+        gpuErrchk(cudaMemcpy(hg.data(), d_gamma, vec * sizeof(linsys_t), cudaMemcpyDeviceToHost));
+        fwrite(hS.data(), sizeof(linsys_t), mat, f);
+        fwrite(hP.data(), sizeof(linsys_t), mat, f);
+        fwrite(hg.data(), sizeof(linsys_t), vec, f);
+    }
+    fclose(f);
+    printf("captured %u system(s): n=%u N=%u offset=%u perturb=%d -> %s\n", count, state_size, knot_points, offset, (int)perturb, argv[3]);
+    return 0;
+}

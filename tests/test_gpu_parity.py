@@ -256,3 +256,25 @@ def test_double_precision_instantiation(torch_cuda, capi, oracle_pcg):
     got = _gpu_solve(torch_cuda, m, d, 0, cap, tol, np.float64)
     want = oracle_pcg.pcg(d["S"][0], d["Pinv"][0], d["gamma"][0], d["lambda0"][0], n, N, cap, tol)
     _assert_same(got, want, "f64")
+
+
+@pytest.mark.parametrize("knots,block", [(32, 128), (32, 64), (128, 128)])
+def test_dropin_headers_reference_launch_geometry(torch_cuda, oracle_pcg, tmp_path, knots, block):
+    """include/gbd_dropin: pcg<float,14,N> launched exactly like include/pcg/sqp.cuh:230 (cooperative,
+    grid = N, block = PCG_NUM_THREADS, smem = pcgSharedMemSize) -- bit-exact vs the oracle."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_build", f"dropin_demo_{knots}")
+    if not os.path.exists(exe):
+        pytest.skip("tests/_build/dropin_demo_* not built (run __graft_entry__.build())")
+    n, cap, tol = 14, 167, 1e-5
+    d = synth.make_systems(n, knots, seed=9, nan_pads=True)
+    fin, fout = tmp_path / "in.bin", tmp_path / "out.bin"
+    np.concatenate([d["S"][0], d["Pinv"][0], d["gamma"][0], d["lambda0"][0]]).astype(np.float32).tofile(fin)
+    subprocess.check_call([exe, str(fin), str(fout), str(cap), repr(tol), str(block), "3"], timeout=120)
+    raw = np.fromfile(fout, np.float32)
+    vec = n * knots
+    tail = raw[3 * vec:].view(np.uint32)
+    got = dict(lam=raw[:vec], r=raw[vec:2 * vec], p=raw[2 * vec:3 * vec], iters=int(tail[0]), max_iter_exit=bool(tail[1]))
+    want = oracle_pcg.pcg(d["S"][0], d["Pinv"][0], d["gamma"][0], d["lambda0"][0], n, knots, cap, tol)
+    _assert_same(got, want, f"drop-in N={knots} block={block}")
