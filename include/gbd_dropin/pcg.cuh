@@ -1,3 +1,147 @@
-// pcg.cuh -- forwarding header of the GBD-PCG drop-in set; everything lives in gpu_pcg.cuh.
+// pcg.cuh -- part of the header-only DROP-IN for the reference's GBD-PCG include directory
+// (see gpu_pcg.cuh for the overview).  Replaces GBD-PCG/include/pcg.cuh: pcgSharedMemSize (:13-20), checkPcgOccupancy (:23-49), pcg<T,n,N> (:54-218).
+// The split into files and what each one defines mirrors the reference, because the reference's other headers
+// include these files individually (include/mpcsim.cuh:19 and include/pcg/linsys_setup.cuh:3 take only
+// "gpuassert.cuh"; include/utils/matrix.cuh:4 takes "utils.cuh") and rely on WHEN the STATE_SIZE / KNOT_POINTS
+// defaults of constants.cuh become visible relative to include/common/settings.cuh.
 #pragma once
-#include "gpu_pcg.cuh"
+#include <cstdint>
+#include <cstdio>
+#include <cuda_runtime.h>
+#include <cooperative_groups.h>
+#include "types.cuh"
+#include "gpuassert.cuh"
+#include "utils.cuh"
+#include "gbd/gbd_grid_pcg.cuh"
+#include "gbd/gbd_cluster_pcg_v3.cuh"
+
+#ifndef GBD_PCG_MAX_BLOCK
+#define GBD_PCG_MAX_BLOCK 256           // upper bound on the caller's block size (register budget of pcg<>)
+#endif
+
+namespace gbd_dropin {
+// shared-memory bytes of gbd::GridPcg<T,n,N,R> / gbd::ClusterPcg3<n,N,N/16,false> as plain functions of run-time sizes
+constexpr size_t a16(size_t x) { return (x + 15) / 16 * 16; }
+constexpr size_t lanes_per_row(size_t n) { return n <= 16 ? 16 : (n <= 32 ? 32 : (n + 31) / 32 * 32); }
+constexpr size_t grid_smem(size_t n, size_t N, size_t R, size_t e)
+{
+    const size_t xs = (n + 3) / 4 * 4;
+    return 16 + 2 * a16(e * R * 3 * n * n) + 2 * a16(e * (R + 2) * xs) + 2 * a16(e * 2 * xs) + a16(e * R * lanes_per_row(n)) + a16(e * N);
+}
+constexpr size_t fast_smem(size_t n, size_t N)
+{
+    const size_t xs = (n + 3) / 4 * 4;
+    return 32 + 2 * a16(4 * 18 * xs) + 3 * a16(4 * 2 * xs) + 2 * a16(4 * N);
+}
+constexpr bool fast_shape(size_t n, size_t N, size_t e)
+{
+#ifdef GBD_DROPIN_NO_CLUSTER
+    return false;
+#else
+    return e == 4 && n % 2 == 0 && n <= 16 && N % 16 == 0 && N / 16 <= 8;
+#endif
+}
+constexpr size_t grid_rows(size_t n, size_t N, size_t e)     // knot rows per CTA of the packet kernel when the block allows
+{
+    return (!fast_shape(n, N, e) && N % 8 == 0 && N / 8 >= 2 && 8 * lanes_per_row(n) <= GBD_PCG_MAX_BLOCK &&
+            grid_smem(n, N, 8, e) <= 48 * 1024) ? 8 : 1;
+}
+// How pcg<T,n,N> is carried out under the reference's launch (cooperative, grid = N CTAs, caller's block size):
+//   FAST  fp32, even n <= 16, N a multiple of 16 with N/16 <= 8 (IIWA: N = 16 .. 128), block >= 128 threads:
+//         the kernel carries compile-time cluster dimensions C = N/16; cluster 0 of the grid runs the
+//         cluster-resident solver (gbd_cluster_pcg_v3.cuh, DSMEM + mbarrier exchange), all other CTAs return.
+//   GRID  everything else: one CTA per RG knot rows exchanges through L2 packets (gbd_grid_pcg.cuh);
+//         RG = 8 when the block has >= 8 row groups of threads, else 1.  CTAs beyond N/RG return.
+template <typename T, uint32_t n, uint32_t N>
+struct Shape {
+    static constexpr bool FAST = fast_shape(n, N, sizeof(T));
+    static constexpr uint32_t C = FAST ? N / 16 : 1;
+    static constexpr uint32_t NT_FAST = 128;
+    static constexpr uint32_t G = n <= 16 ? 16 : (n <= 32 ? 32 : (n + 31) / 32 * 32);
+    static constexpr uint32_t RG = (uint32_t)grid_rows(n, N, sizeof(T));
+    using Fast = gbd::ClusterPcg3<FAST ? n : 2, FAST ? N : 16, FAST ? C : 1, false>;
+    static constexpr size_t SMEM_FAST = FAST ? Fast::SMEM_BYTES : 0;
+    static_assert(!FAST || Fast::SMEM_BYTES == fast_smem(n, N), "run-time smem formula out of sync");
+    static_assert(gbd::GridPcg<T, n, N, 1>::SMEM_BYTES == grid_smem(n, N, 1, sizeof(T)), "run-time smem formula out of sync");
+    static constexpr size_t SMEM_G1 = gbd::GridPcg<T, n, N, 1>::SMEM_BYTES;
+    static constexpr size_t SMEM_GR = gbd::GridPcg<T, n, N, RG>::SMEM_BYTES;
+    static constexpr size_t SMEM_BYTES = SMEM_FAST > (SMEM_G1 > SMEM_GR ? SMEM_G1 : SMEM_GR) ? SMEM_FAST : (SMEM_G1 > SMEM_GR ? SMEM_G1 : SMEM_GR);
+};
+// packet workspace + epoch counter of one instantiation (zero-initialised by the loader); R = 1 is the largest layout
+template <typename T, uint32_t n, uint32_t N>
+__device__ unsigned long long g_ws[gbd::GridPcg<T, n, N, 1>::WS_WORDS];
+template <typename T, uint32_t n, uint32_t N>
+__device__ uint32_t g_epoch;
+}  // namespace gbd_dropin
+
+template <typename T, uint32_t state_size, uint32_t knot_points>
+__global__ void __cluster_dims__(gbd_dropin::Shape<T, state_size, knot_points>::C, 1, 1) __launch_bounds__(GBD_PCG_MAX_BLOCK)
+pcg(T *d_S, T *d_Pinv, T *d_gamma, T *d_lambda, T *d_r, T *d_p, T *d_v_temp, T *d_eta_new_temp, uint32_t *d_iters,
+    bool *d_max_iter_exit, uint32_t max_iter, T exit_tol)
+{
+    using SH = gbd_dropin::Shape<T, state_size, knot_points>;
+    extern __shared__ __align__(16) unsigned char gbd_dropin_smem[];
+    (void)d_v_temp; (void)d_eta_new_temp;          // reference scratch for its smem trees; not needed here
+    uint8_t *d_flag = reinterpret_cast<uint8_t *>(d_max_iter_exit);
+    if constexpr (SH::FAST) {
+        if (blockDim.x >= SH::NT_FAST) {
+            if (gbd::cluster_idx() != 0) return;                  // whole clusters leave together
+            gbd::PcgArgs<float> a{d_S, d_Pinv, d_gamma, d_lambda, d_r, d_p, d_iters, d_flag, 1u, max_iter, exit_tol, 0u};
+            gbd::pcg_cluster_v3_init<state_size, knot_points, SH::C, false>(gbd_dropin_smem);
+            __syncthreads();
+            gbd::cluster_sync();
+            if (threadIdx.x < SH::NT_FAST) gbd::pcg_cluster_v3_run<state_size, knot_points, SH::C, false>(a, gbd_dropin_smem, 0u, 1u);
+            gbd::cluster_sync();
+            return;
+        }
+    }
+    const uint32_t base = gbd_dropin::g_epoch<T, state_size, knot_points>;
+    const bool tma = ((((uintptr_t)d_S) | ((uintptr_t)d_Pinv)) & 15u) == 0;
+    unsigned long long *ws = gbd_dropin::g_ws<T, state_size, knot_points>;
+    uint32_t last;
+    if (SH::RG > 1 && blockDim.x >= SH::RG * SH::G) {
+        if (blockIdx.x >= knot_points / SH::RG) return;
+        last = gbd::pcg_grid_body<T, state_size, knot_points, SH::RG>(d_S, d_Pinv, d_gamma, d_lambda, d_r, d_p, d_iters, d_flag, max_iter,
+                                                                     exit_tol, ws, base, tma, gbd_dropin_smem);
+    } else {
+        last = gbd::pcg_grid_body<T, state_size, knot_points, 1>(d_S, d_Pinv, d_gamma, d_lambda, d_r, d_p, d_iters, d_flag, max_iter,
+                                                                exit_tol, ws, base, tma, gbd_dropin_smem);
+    }
+    // every working CTA has read `base` before CTA 0 can get here (it needed all of their packets)
+    if (blockIdx.x == 0 && threadIdx.x == 0) gbd_dropin::g_epoch<T, state_size, knot_points> = last;
+}
+
+// Dynamic shared memory the launch site must pass (pcg.cuh:13-20 in the reference).  Run-time mirror of
+// gbd_dropin::Shape<T,n,N>::SMEM_BYTES: the largest of the three bodies' layouts; always < 48 KB for n <= 32.
+template <typename T>
+size_t pcgSharedMemSize(uint32_t state_size, uint32_t knot_points)
+{
+    const size_t n = state_size, N = knot_points, e = sizeof(T);
+    size_t need = gbd_dropin::grid_smem(n, N, 1, e);
+    if (gbd_dropin::fast_shape(n, N, e) && gbd_dropin::fast_smem(n, N) > need) need = gbd_dropin::fast_smem(n, N);
+    const size_t rg = gbd_dropin::grid_rows(n, N, e);
+    if (rg > 1 && gbd_dropin::grid_smem(n, N, rg, e) > need) need = gbd_dropin::grid_smem(n, N, rg, e);
+    return need;
+}
+
+template <typename T>
+bool checkPcgOccupancy(void *kernel, dim3 block, uint32_t state_size, uint32_t knot_points)
+{
+    const size_t smem = pcgSharedMemSize<T>(state_size, knot_points);
+    int dev = 0, coop = 0, sms = 0, per_sm = 0;
+    gpuErrchk(cudaGetDevice(&dev));
+    gpuErrchk(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    gpuErrchk(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (!coop) {
+        printf("[Error] Device does not support Cooperative Threads\n");
+        return false;
+    }
+    if (smem > 48 * 1024) gpuErrchk(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gpuErrchk(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, (int)(block.x * block.y * block.z), smem));
+    if ((int)knot_points > sms * per_sm) {
+        printf("Too many knot points ([%d]). Device supports [%d] active blocks, over [%d] SMs.\n", knot_points,
+               sms * per_sm, sms);
+        return false;
+    }
+    return true;
+}

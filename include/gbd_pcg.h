@@ -52,7 +52,8 @@ int gbd_pcg_variant_at(int i, uint32_t *n, uint32_t *N, uint32_t *cluster, int *
 
 /* Tuning knob: pick the cluster size (CTAs per system) and kernel build used for (n, N).
  * mode: 0 = v1 kernel, tiles in shared memory; 1 = v1, tiles in registers; 2 = v2 kernel (st.async +
- * mbarrier signalling), 1 CTA/SM register budget; 3 = v2, 2 CTAs/SM budget (default for batches).
+ * mbarrier signalling), 1 CTA/SM register budget; 3 = v2, 2 CTAs/SM budget; 4 = grid kernel (whole GPU on
+ * one system, L2 packets); 5 = v3 kernel (two matrix rows per thread), 1 CTA/SM budget; 6 = v3, 2 CTAs/SM.
  * cluster = 0 and mode = -1 restore the built-in default.  All modes give bit-identical results. */
 int gbd_pcg_set_tuning(uint32_t n, uint32_t N, int is_f64, uint32_t cluster, int mode);
 

@@ -12,6 +12,7 @@
 
 #include "../../include/gbd_pcg.h"
 #include "../../include/gbd/gbd_grid_pcg.cuh"
+#include "../../include/gbd/gbd_cluster_pcg_v3.cuh"
 #include <map>
 
 namespace {
@@ -21,6 +22,7 @@ using namespace gbd;
 // mode: 0 = v1 kernel, tiles in shared memory; 1 = v1 kernel, tiles in registers;
 //       2 = v2 kernel (st.async/mbarrier signalling), 1 CTA/SM register budget; 3 = v2, 2 CTAs/SM budget;
 //       4 = grid kernel (whole GPU on one system, packets through L2; C then holds the CTA count)
+//       5 = v3 kernel (two matrix rows per thread, 8-lane knot rows), 1 CTA/SM register budget; 6 = v3, 2 CTAs/SM
 struct Variant {
     uint32_t n, N, C;
     int mode;
@@ -48,6 +50,13 @@ Variant make_v2()
                    (const void *)pcg_cluster_kernel_v2<T, n, N, C, MINB>, false, 0};
 }
 
+template <uint32_t n, uint32_t N, uint32_t C, uint32_t MINB>
+Variant make_v3()
+{
+    using K = ClusterPcg3<n, N, C, true>;
+    return Variant{n, N, C, MINB == 1 ? 5 : 6, false, K::NT, K::SMEM_BYTES, (const void *)pcg_cluster_kernel_v3<n, N, C, MINB>, false, 0};
+}
+
 template <typename T, uint32_t n, uint32_t N, uint32_t R>
 Variant make_grid()
 {
@@ -62,16 +71,30 @@ Variant make_grid()
 std::vector<Variant> &variants()
 {
     static std::vector<Variant> v = {
-        make_v2<float, 14, 128, 8, 1>(),          make_v2<float, 14, 128, 8, 2>(),
+        // defaults first (measured on B200, profiles/r01_ab_bench_v3.json): v2 for single solves up to N = 256,
+        // v3 at N = 512; among the 2-CTA/SM builds (the batched default) v3 comes first
+        make_v2<float, 14, 128, 8, 1>(),          make_v3<14, 128, 8, 2>(),
+        make_v2<float, 14, 128, 8, 2>(),
         make_v2<float, 14, 128, 16, 1>(),         make_v2<float, 14, 128, 4, 1>(),
-        make_v2<float, 14, 32, 4, 1>(),           make_v2<float, 14, 32, 8, 1>(),
+        make_v2<float, 14, 32, 4, 1>(),           make_v3<14, 32, 1, 2>(),
+        make_v2<float, 14, 32, 8, 1>(),
         make_v2<float, 14, 32, 2, 1>(),           make_v2<float, 14, 32, 4, 2>(),
         make_v2<float, 14, 64, 8, 1>(),           make_v2<float, 14, 64, 4, 1>(),
+        make_v3<14, 64, 2, 2>(),
         make_v2<float, 14, 256, 16, 1>(),         make_v2<float, 14, 256, 8, 1>(),
-        make_v2<float, 14, 512, 16, 1>(),
+        make_v3<14, 512, 16, 1>(),                make_v2<float, 14, 512, 16, 1>(),
         make_v2<float, 14, 16, 4, 1>(),           make_v2<float, 14, 8, 8, 1>(),
         make_v2<float, 6, 12, 4, 1>(),            make_v2<float, 6, 12, 1, 2>(),
         make_v2<float, 2, 3, 1, 1>(),             make_v2<float, 2, 3, 3, 1>(),
+        make_v3<14, 128, 8, 1>(),
+        make_v3<14, 128, 16, 1>(),                make_v3<14, 128, 4, 1>(),
+        make_v3<14, 32, 2, 1>(),                  make_v3<14, 32, 4, 1>(),
+        make_v3<14, 32, 1, 1>(),                  make_v3<14, 32, 2, 2>(),
+        make_v3<14, 64, 4, 1>(),                  make_v3<14, 64, 8, 1>(),
+        make_v3<14, 64, 2, 1>(),
+        make_v3<14, 256, 16, 1>(),                make_v3<14, 256, 8, 1>(),
+        make_v3<14, 16, 2, 1>(),                  make_v3<14, 16, 1, 1>(),
+        make_v3<6, 12, 3, 1>(),
         make_variant<float, 14, 128, 8, true>(),  make_variant<float, 14, 128, 16, true>(),
         make_variant<float, 14, 128, 4, true>(),  make_variant<float, 14, 128, 8, false>(),
         make_variant<float, 14, 32, 4, true>(),   make_variant<float, 14, 32, 8, true>(),
@@ -119,7 +142,7 @@ Variant *find_variant(uint32_t n, uint32_t N, bool f64, bool batched)
     for (auto &v : variants()) {
         if (v.n != n || v.N != N || v.f64 != f64) continue;
         if (!first) first = &v;
-        if (!first_b && v.mode == 3) first_b = &v;      // 2-CTA/SM build: the default for batched launches
+        if (!first_b && (v.mode == 3 || v.mode == 6)) first_b = &v;      // 2-CTA/SM build: the default for batched launches
         if ((wantC || wantMode >= 0) && (wantC == 0 || v.C == wantC) && (wantMode < 0 || v.mode == wantMode)) return &v;
     }
     if (wantC || wantMode >= 0) return nullptr;

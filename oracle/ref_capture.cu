@@ -7,7 +7,10 @@
 // then form_schur_system at rho = 1e-3, and writes (S, Pinv, gamma) of each requested system as raw
 // float32.  d_S / d_Pinv are pre-filled with 0xFF bytes (NaN) so the pad tiles the reference never
 // writes are visibly garbage.
-//   ref_capture <traj.csv> <eepos.traj> <out.bin> <knot offset> <count> <perturb 0|1>
+//   ref_capture <traj.csv> <eepos.traj> <out.bin> <knot offset> <count> <perturb 0|1> [mode bits]
+// mode bits (debug aid): 1 = do not pre-fill S/Pinv with 0xFF; 2 = run compute_merit first as sqp.cuh:173 does;
+// 4 = create the cuBLAS handle and 8 streams first as sqp.cuh:64-72 does; 8 = run the PCG kernel after the assembly
+// exactly as sqp.cuh:230 launches it and append lambda (n*N floats), iters, flag to the record.
 // count > 1 with perturb = 1 builds BASELINE config 4's batch: system i = the window at <offset> plus
 // N(0, 0.05^2) on q, N(0, 0.01^2) on qd, N(0, 1) on u, std::mt19937_64(1234 + i).
 #include <cstdio>
@@ -58,6 +61,25 @@ int main(int argc, char **argv)
     gpuErrchk(cudaMemcpy(d_ee, ee.data(), 6 * knot_points * sizeof(linsys_t), cudaMemcpyHostToDevice));
     void *d_dynmem = gato_plant::initializeDynamicsConstMem<linsys_t>();
     linsys_t rho = 1e-3;
+    const int mode = argc > 7 ? atoi(argv[7]) : 0;
+    cudaStream_t streams[8];
+    cublasHandle_t handle;
+    if (mode & 4) {
+        for (int i = 0; i < 8; i++) cudaStreamCreate(&streams[i]);
+        if (cublasCreate(&handle) != CUBLAS_STATUS_SUCCESS) return 13;
+    }
+    linsys_t *d_merit, *d_lambda, *d_r, *d_p, *d_v, *d_e;
+    uint32_t *d_it;
+    bool *d_fl;
+    gpuErrchk(cudaMalloc(&d_merit, sizeof(linsys_t)));
+    gpuErrchk(cudaMemset(d_merit, 0, sizeof(linsys_t)));
+    gpuErrchk(cudaMalloc(&d_lambda, vec * sizeof(linsys_t)));
+    gpuErrchk(cudaMalloc(&d_r, vec * sizeof(linsys_t)));
+    gpuErrchk(cudaMalloc(&d_p, vec * sizeof(linsys_t)));
+    gpuErrchk(cudaMalloc(&d_v, knot_points * sizeof(linsys_t)));
+    gpuErrchk(cudaMalloc(&d_e, knot_points * sizeof(linsys_t)));
+    gpuErrchk(cudaMalloc(&d_it, sizeof(uint32_t)));
+    gpuErrchk(cudaMalloc(&d_fl, sizeof(bool)));
 
     FILE *f = fopen(argv[3], "wb");
     std::vector<linsys_t> hS(mat), hP(mat), hg(vec);
@@ -76,8 +98,15 @@ int main(int argc, char **argv)
         }
         gpuErrchk(cudaMemcpy(d_xu, xu.data(), traj_len * sizeof(linsys_t), cudaMemcpyHostToDevice));
         gpuErrchk(cudaMemcpy(d_xs, xu.data(), state_size * sizeof(linsys_t), cudaMemcpyHostToDevice));
-        gpuErrchk(cudaMemset(d_S, 0xFF, mat * sizeof(linsys_t)));
-        gpuErrchk(cudaMemset(d_Pinv, 0xFF, mat * sizeof(linsys_t)));
+        if (!(mode & 1)) {
+            gpuErrchk(cudaMemset(d_S, 0xFF, mat * sizeof(linsys_t)));
+            gpuErrchk(cudaMemset(d_Pinv, 0xFF, mat * sizeof(linsys_t)));
+        }
+        if (mode & 2) {
+            compute_merit<linsys_t><<<knot_points, MERIT_THREADS, get_merit_smem_size<linsys_t>(state_size, control_size)>>>(
+                state_size, control_size, knot_points, d_xu, d_ee, static_cast<linsys_t>(10), timestep, d_dynmem, d_merit);
+            gpuErrchk(cudaPeekAtLastError());
+        }
         generate_kkt_submatrices<linsys_t><<<knot_points, KKT_THREADS, 2 * get_kkt_smem_size<linsys_t>(state_size, control_size)>>>(
             state_size, control_size, knot_points, d_G, d_C, d_g, d_c, d_dynmem, timestep, d_ee, d_xs, d_xu);
         gpuErrchk(cudaPeekAtLastError());
@@ -90,6 +119,25 @@ int main(int argc, char **argv)
         fwrite(hS.data(), sizeof(linsys_t), mat, f);
         fwrite(hP.data(), sizeof(linsys_t), mat, f);
         fwrite(hg.data(), sizeof(linsys_t), vec, f);
+        if (mode & 8) {
+            pcg_config<linsys_t> config;
+            config.pcg_exit_tol = 1e-4;
+            config.pcg_max_iter = PCG_MAX_ITER;
+            gpuErrchk(cudaMemset(d_lambda, 0, vec * sizeof(linsys_t)));
+            void *pcg_kernel = (void *)pcg<linsys_t, STATE_SIZE, KNOT_POINTS>;
+            void *args[] = {(void *)&d_S, (void *)&d_Pinv, (void *)&d_gamma, (void *)&d_lambda, (void *)&d_r, (void *)&d_p, (void *)&d_v,
+                            (void *)&d_e, (void *)&d_it, (void *)&d_fl, (void *)&config.pcg_max_iter, (void *)&config.pcg_exit_tol};
+            gpuErrchk(cudaLaunchCooperativeKernel(pcg_kernel, knot_points, PCG_NUM_THREADS, args, pcgSharedMemSize<linsys_t>(state_size, knot_points)));
+            uint32_t it = 0;
+            bool fl = false;
+            gpuErrchk(cudaMemcpy(&it, d_it, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+            gpuErrchk(cudaMemcpy(&fl, d_fl, sizeof(bool), cudaMemcpyDeviceToHost));
+            gpuErrchk(cudaMemcpy(hg.data(), d_lambda, vec * sizeof(linsys_t), cudaMemcpyDeviceToHost));
+            fwrite(hg.data(), sizeof(linsys_t), vec, f);
+            uint32_t tail[2] = {it, (uint32_t)fl};
+            fwrite(tail, sizeof(uint32_t), 2, f);
+            printf("  pcg: iters %u max_iter_exit %d\n", it, (int)fl);
+        }
     }
     fclose(f);
     printf("captured %u system(s): n=%u N=%u offset=%u perturb=%d -> %s\n", count, state_size, knot_points, offset, (int)perturb, argv[3]);

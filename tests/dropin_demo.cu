@@ -47,7 +47,7 @@ int main(int argc, char **argv)
                              (void *)&d_v_temp, (void *)&d_eta_new_temp, (void *)&d_pcg_iters, (void *)&d_pcg_exit,
                              (void *)&config.pcg_max_iter, (void *)&config.pcg_exit_tol};
     const size_t smem = pcgSharedMemSize<float>(n, N);
-    if (smem != gbd::GridPcg<float, STATE_SIZE, KNOT_POINTS, 1>::SMEM_BYTES) { fprintf(stderr, "smem size mismatch\n"); return 5; }
+    if (smem != gbd_dropin::Shape<float, STATE_SIZE, KNOT_POINTS>::SMEM_BYTES) { fprintf(stderr, "smem size mismatch\n"); return 5; }
 
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);

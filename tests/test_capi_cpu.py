@@ -104,3 +104,35 @@ def test_synth_layout_and_roofline_bytes():
     np.testing.assert_array_equal(T[:, :-1, 2], np.swapaxes(T[:, 1:, 0], -1, -2))
     # negated (negative definite) storage convention
     assert (np.diagonal(T[:, :, 1], axis1=-2, axis2=-1) < 0).all()
+
+
+def _pcg_instantiations(binary):
+    out = subprocess.run(["cuobjdump", "-res-usage", binary], capture_output=True, text=True).stdout
+    return sorted(set(re.findall(r"Function (_Z3pcgI\w+?EEv)", out)))
+
+
+def test_dropin_build_instantiates_the_reference_shapes():
+    """Regression for an include-order bug: the reference's headers include "gpuassert.cuh" / "utils.cuh"
+    BEFORE include/common/settings.cuh defines STATE_SIZE, so a drop-in file that defines more than its
+    namesake (e.g. the STATE_SIZE default of constants.cuh) silently turns sqp.cuh's
+    pcg<T,STATE_SIZE,KNOT_POINTS> into pcg<float,3,N>.  The reference example built against the drop-in
+    headers must contain exactly the pcg<> instantiations of the build against GBD-PCG/include."""
+    run = os.path.join(ROOT, "oracle", "_ref", "run")
+    pairs = [(os.path.join(run, f"track_iiwa_pcg_ref_{k}"), os.path.join(run, f"track_iiwa_pcg_dropin_{k}")) for k in (32, 128)]
+    pairs = [p for p in pairs if os.path.exists(p[0]) and os.path.exists(p[1])]
+    if not pairs:
+        pytest.skip("oracle/_ref/run/track_iiwa_pcg_* not built (make -C oracle examples; needs /root/reference)")
+    for ref, drop in pairs:
+        want = _pcg_instantiations(ref)
+        assert want and all("Lj14E" in w for w in want), want
+        assert _pcg_instantiations(drop) == want
+
+
+def test_dropin_headers_define_what_their_namesakes_define():
+    """gpuassert.cuh must not leak STATE_SIZE / KNOT_POINTS; constants.cuh must (as defaults only)."""
+    inc = os.path.join(ROOT, "include", "gbd_dropin")
+    src = "#include \"%s\"\n#if defined(STATE_SIZE) || defined(KNOT_POINTS)\n#error leaked\n#endif\nint main(){return 0;}\n"
+    for hdr, leaks in (("gpuassert.cuh", False), ("constants.cuh", True), ("types.cuh", True), ("utils.cuh", True)):
+        p = subprocess.run(["/usr/local/cuda/bin/nvcc", "-std=c++17", "-E", "-x", "cu", "-I" + inc, "-I" + os.path.join(ROOT, "include"),
+                            "-"], input=src % hdr, capture_output=True, text=True)
+        assert (p.returncode != 0) == leaks, (hdr, p.stderr[-300:])
