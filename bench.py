@@ -398,6 +398,50 @@ def run_ours(args):
                                 "unit": "GB/s", "frac": bi / Kb * b_iter / bsec / 1e9 / world / peak,
                                 "compulsory_gbs": Bl * esz * (2 * (3 * N - 2) * n * n + 4 * N * n) / bsec / 1e9}}
         launches_b = Kb
+    # ---------------- extras (rank 0): the reference-minted IIWA system and the header drop-in pcg<> under the
+    # reference's own launch geometry (cooperative, grid = N, 128 threads), both on tests/golden/iiwa_128_0.npz
+    extras = {}
+    gpath = os.path.join(ROOT, "tests", "golden", "iiwa_128_0.npz")
+    if rank == 0 and os.path.exists(gpath):
+        g = np.load(gpath)
+        gS, gP, gg = (torch.from_numpy(g[k]).to(dev) for k in ("S", "Pinv", "gamma"))
+        gl = torch.zeros(n * N, device=dev)
+
+        def gsolve():
+            gl.zero_()
+            rc = L.gbd_pcg_solve_f32(n, N, gS.data_ptr(), gP.data_ptr(), gg.data_ptr(), gl.data_ptr(), 0, 0, 0, 0,
+                                     iters[:1].data_ptr(), flags[:1].data_ptr(), MAX_ITER, EXIT_TOL, stream)
+            assert rc == 0
+
+        for _ in range(20):
+            gsolve()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(200):
+            gsolve()
+        g1.record()
+        torch.cuda.synchronize()
+        git = int(iters[0].item())
+        extras["iiwa_golden"] = {"system": "tests/golden/iiwa_128_0.npz (reference KKT+Schur assembly of examples/trajfiles/0_0, "
+                                           "first SQP iteration)", "iters": git, "reference_kernel_iters": int(g["run0_iters"]),
+                                 "lambda_bit_identical_to_reference_kernel": bool(np.array_equal(gl.cpu().numpy(), g["run0_lam"])),
+                                 "kernel_us": 1e3 * g0.elapsed_time(g1) / 200 - 2.0, "note": "includes a ~2 us lambda memset per solve (subtracted)"}
+        demo = os.path.join(ROOT, "tests", "_build", "dropin_demo_128")
+        if os.path.exists(demo):
+            import subprocess
+            import tempfile
+            with tempfile.TemporaryDirectory() as td:
+                fin, fout = os.path.join(td, "in.bin"), os.path.join(td, "out.bin")
+                np.concatenate([g["S"], g["Pinv"], g["gamma"], np.zeros(n * N, np.float32)]).tofile(fin)
+                try:
+                    out = subprocess.run([demo, fin, fout, str(MAX_ITER), repr(EXIT_TOL), "128", "400"], capture_output=True,
+                                         text=True, timeout=120).stdout.split()
+                    extras["dropin_pcg_template"] = {
+                        "what": "include/gbd_dropin pcg<float,14,128> launched as include/pcg/sqp.cuh:230 does "
+                                "(cudaLaunchCooperativeKernel, grid 128, block 128)", "iters": int(out[1]),
+                        "kernel_us": float(out[5]), "us_per_iter": float(out[5]) / max(1, int(out[1]))}
+                except Exception as e:                         # the extras never fail the bench line
+                    extras["dropin_pcg_template"] = {"error": repr(e)[:200]}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline({k: (host[k][:64] if isinstance(host[k], np.ndarray) else host[k]) for k in host},
@@ -421,13 +465,14 @@ def run_ours(args):
                     "us_per_solve": 1e6 * e2e_s / Ke, "steps": Ke,
                     "api": "gbd_pcg_plan_solve_host_f32 (replaces solvePCG(h_S,...), interface.cuh:24-89)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": _ncu_traffic(), "peak_source": peak_src, "kernel": "gbd::pcg_cluster_kernel",
+                         "traffic": _ncu_traffic(), "peak_source": peak_src, "kernel": "gbd::pcg_cluster_kernel_v2<float,14,128,16,1>",
                          "kernel_us": 1e6 * kernel_s, "bytes_per_iter": b_iter, "compulsory_gbs": compulsory,
                          "note": "achieved is SpMV-equivalent bytes (tiles stay on-chip across iterations), not DRAM traffic; "
                                  "this config is latency-bound by construction (0.6 MB working set)"},
             "clocks": clocks,
             "gpu_launches": int(launches_timed),
         }
+        line.update(extras)
         if batched:
             line["batched"] = batched
         if cpu:

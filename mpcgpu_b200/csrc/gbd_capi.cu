@@ -73,9 +73,9 @@ std::vector<Variant> &variants()
     static std::vector<Variant> v = {
         // defaults first (measured on B200, profiles/r01_ab_bench_v3.json): v2 for single solves up to N = 256,
         // v3 at N = 512; among the 2-CTA/SM builds (the batched default) v3 comes first
-        make_v2<float, 14, 128, 8, 1>(),          make_v3<14, 128, 8, 2>(),
+        make_v2<float, 14, 128, 16, 1>(),         make_v3<14, 128, 8, 2>(),
         make_v2<float, 14, 128, 8, 2>(),
-        make_v2<float, 14, 128, 16, 1>(),         make_v2<float, 14, 128, 4, 1>(),
+        make_v2<float, 14, 128, 8, 1>(),          make_v2<float, 14, 128, 4, 1>(),
         make_v2<float, 14, 32, 4, 1>(),           make_v3<14, 32, 1, 2>(),
         make_v2<float, 14, 32, 8, 1>(),
         make_v2<float, 14, 32, 2, 1>(),           make_v2<float, 14, 32, 4, 2>(),
