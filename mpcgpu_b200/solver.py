@@ -110,6 +110,7 @@ class HostPlan:
         if self.dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
             raise TypeError("float32 or float64")
         self._h = C.c_void_p()
+        self._fn = None
         _capi.check(_capi.lib().gbd_pcg_plan_create(state_size, knot_points, batch, int(self.dtype == np.float64),
                                                     C.byref(self._h)), "gbd_pcg_plan_create")
 
@@ -138,6 +139,21 @@ class HostPlan:
         _capi.check(fn(self._h, h_S.ctypes.data, h_Pinv.ctypes.data, h_gamma.ctypes.data, h_lambda.ctypes.data,
                        int(max_iter), float(exit_tol), iters.ctypes.data, flags.ctypes.data), "gbd_pcg_plan_solve_host")
         return iters, flags.astype(bool)
+
+
+    def solve_raw(self, p_S: int, p_Pinv: int, p_gamma: int, p_lambda: int, max_iter: int, exit_tol: float):
+        """Same call with raw host addresses (the caller guarantees dtype / size / contiguity): what a C++ host
+        passes.  Returns the iteration count of system 0; per-system results are in self.iters / self.flags."""
+        if self._fn is None:
+            self._fn = (_capi.lib().gbd_pcg_plan_solve_host_f64 if self.dtype == np.float64
+                        else _capi.lib().gbd_pcg_plan_solve_host_f32)
+            self.iters = np.zeros(self.batch, np.uint32)
+            self.flags = np.zeros(self.batch, np.uint8)
+            self._pi, self._pf = self.iters.ctypes.data, self.flags.ctypes.data
+        rc = self._fn(self._h, p_S, p_Pinv, p_gamma, p_lambda, max_iter, exit_tol, self._pi, self._pf)
+        if rc:
+            _capi.check(rc, "gbd_pcg_plan_solve_host")
+        return int(self.iters[0])
 
 
 _plans: dict = {}
