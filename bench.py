@@ -445,6 +445,47 @@ def run_ours(args):
                         "kernel_us": float(out[5]), "us_per_iter": float(out[5]) / max(1, int(out[1]))}
                 except Exception as e:                         # the extras never fail the bench line
                     extras["dropin_pcg_template"] = {"error": repr(e)[:200]}
+    # ---------------- the other BASELINE.json configs (rank 0, short): kernel time per solve and SpMV-equivalent GB/s
+    if rank == 0 and not args.no_configs:
+        others = []
+        for (cn, cN, ccap, ctol, what) in ((14, 32, 173, 1e-4, "configs[0] size on the GPU (n=14, N=32)"),
+                                           (14, 512, 67, 1e-4, "configs[2] long horizon (n=14, N=512)"),
+                                           (64, 256, 200, 1e-6, "configs[4] synthetic block=64, N=256, tol 1e-6, cap 200")):
+            try:
+                nsys = 8 if cn == 14 else 2
+                hc = synth.make_systems(cn, cN, batch=nsys, seed=4242)
+                cS, cP, cg = (torch.from_numpy(hc[k]).to(dev) for k in ("S", "Pinv", "gamma"))
+                reps = 64 if cn == 14 else 16
+                cl = torch.zeros(reps + 4, cn * cN, device=dev)
+                cit = torch.zeros(reps + 4, dtype=torch.int32, device=dev)
+                cfl = torch.zeros(reps + 4, dtype=torch.uint8, device=dev)
+
+                def csolve(q):
+                    i = q % nsys
+                    rc = L.gbd_pcg_solve_f32(cn, cN, cS[i].data_ptr(), cP[i].data_ptr(), cg[i].data_ptr(), cl[q].data_ptr(), 0, 0,
+                                             0, 0, cit[q:].data_ptr(), cfl[q:].data_ptr(), ccap, ctol, stream)
+                    if rc:
+                        raise _capi.GbdPcgError(rc, "gbd_pcg_solve_f32")
+
+                for q in range(4):
+                    csolve(q)
+                torch.cuda.synchronize()
+                c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                c0.record()
+                for q in range(4, reps + 4):
+                    csolve(q)
+                c1.record()
+                torch.cuda.synchronize()
+                us = 1e3 * c0.elapsed_time(c1) / reps
+                mit = float(cit[4:].float().mean().item())
+                bi = synth.bytes_per_iteration(cn, cN, esz)
+                others.append({"config": what, "kernel_us": us, "mean_iters": mit, "us_per_iter": us / max(mit, 1.0),
+                               "pcg_iters_per_sec": mit / (us * 1e-6), "converged_frac": float((cfl[4:] == 0).float().mean().item()),
+                               "spmv_equiv_gbs": mit * bi / (us * 1e-6) / 1e9, "frac_of_hbm_peak": mit * bi / (us * 1e-6) / 1e9 / peak,
+                               "bytes_per_iter": bi, "tiles_resident_on_chip": True})
+            except Exception as e:                             # the extras never fail the bench line
+                others.append({"config": what, "error": repr(e)[:200]})
+        extras["other_configs"] = others
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline({k: (host[k][:64] if isinstance(host[k], np.ndarray) else host[k]) for k in host},
@@ -496,6 +537,7 @@ def main():
     ap.add_argument("--batched-steps", type=int, default=5)
     ap.add_argument("--no-batched", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the short legs for BASELINE.json configs 0, 2 and 4")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--prewarm", type=float, default=0.5, help="seconds of untimed solves before the W warm-up steps")
     args = ap.parse_args()

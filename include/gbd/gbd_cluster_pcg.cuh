@@ -43,6 +43,7 @@ struct PcgArgs {
     uint32_t max_iter;
     T exit_tol;
     uint32_t use_tma;  // 0: plain loads (unaligned pointers)
+    uint32_t *dbg = nullptr;   // timeline build only (gbd_pcg_set_debug_buffer): per-thread %clock stamps
 };
 
 template <typename T, uint32_t n, uint32_t N, uint32_t C, bool REGS>

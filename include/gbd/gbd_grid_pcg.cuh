@@ -78,8 +78,13 @@ struct GridPcg {
     static constexpr uint32_t XLEN = (R + 2) * XS;
     static constexpr bool TMA_OK = (TILE * sizeof(T)) % 16 == 0;
     static constexpr uint32_t PW = Pkt<T>::WORDS;
-    // workspace (u64 words): per phase type {A, B}: N partial packets + per CTA {first row, last row} of n packets
-    static constexpr size_t PH_WORDS = (size_t)PW * (N + 2 * (size_t)CTAS * n);
+    // workspace (u64 words): per phase type {A, B}, per CONSUMER CTA a private region of N partial packets + the
+    // left neighbour's last row + the right neighbour's first row (n packets each).  Producers write one copy of
+    // a partial per consumer, so no line is ever polled by more than one CTA: with one shared copy all CTAS x NT
+    // threads spin on the same N/16 lines and the L2 slice serialises them (measured, tools/micro/l2_exchange.cu:
+    // 7200 -> 3000 cycles per all-gather at 128 CTAs, N = 256).
+    static constexpr size_t REGION_WORDS = (size_t)PW * (N + 2 * n);
+    static constexpr size_t PH_WORDS = REGION_WORDS * CTAS;
     static constexpr size_t WS_WORDS = 2 * PH_WORDS;
     static constexpr size_t align16(size_t x) { return (x + 15) / 16 * 16; }
     static constexpr size_t OFF_BAR = 0;
@@ -99,10 +104,28 @@ template <typename T, uint32_t n, uint32_t XS>
 __device__ __forceinline__ T chain_padded_smem(const T *__restrict__ mrow, const T *__restrict__ xw)
 {
     T acc = T(0);
+    constexpr uint32_t V = 16 / sizeof(T);              // vector elements per 128-bit window load
+    constexpr uint32_t CB = 4 * V;                       // columns per register block of the window
 #pragma unroll
     for (uint32_t blk = 0; blk < 3; ++blk) {
-#pragma unroll 16
-        for (uint32_t c = 0; c < n; ++c) acc = fma_rn(mrow[(blk * n + c) * n], xw[blk * XS + c], acc);
+#pragma unroll 1
+        for (uint32_t c0 = 0; c0 + CB <= n; c0 += CB) {
+            T x[CB];
+#pragma unroll
+            for (uint32_t q = 0; q < 4; ++q) {
+                if constexpr (sizeof(T) == 4) {
+                    const float4 f = *reinterpret_cast<const float4 *>(xw + blk * XS + c0 + 4 * q);
+                    x[4 * q] = f.x; x[4 * q + 1] = f.y; x[4 * q + 2] = f.z; x[4 * q + 3] = f.w;
+                } else {
+                    const double2 f = *reinterpret_cast<const double2 *>(xw + blk * XS + c0 + 2 * q);
+                    x[2 * q] = f.x; x[2 * q + 1] = f.y;
+                }
+            }
+#pragma unroll
+            for (uint32_t c = 0; c < CB; ++c) acc = fma_rn(mrow[(blk * n + c0 + c) * n], x[c], acc);
+        }
+#pragma unroll 4
+        for (uint32_t c = n / CB * CB; c < n; ++c) acc = fma_rn(mrow[(blk * n + c) * n], xw[blk * XS + c], acc);
     }
     return acc;
 }
@@ -141,27 +164,83 @@ __device__ __forceinline__ uint32_t pcg_grid_body(const T *__restrict__ gS_all, 
     const bool own_lhalo = group_live && g == 0 && j < n, own_rhalo = group_live && g == R - 1 && j < n;
 
     unsigned long long *wsA = ws, *wsB = ws + K::PH_WORDS;
-    auto part_slot = [&](unsigned long long *base, uint32_t i) { return base + (size_t)PW * i; };
+    // region of consumer CTA c: [N partials | n from its left neighbour | n from its right neighbour]
+    auto part_slot = [&](unsigned long long *base, uint32_t c, uint32_t i) { return base + K::REGION_WORDS * c + (size_t)PW * i; };
     auto row_slot = [&](unsigned long long *base, uint32_t c, uint32_t which, uint32_t e) {
-        return base + (size_t)PW * (N + ((size_t)c * 2 + which) * n + e);
+        return base + K::REGION_WORDS * c + (size_t)PW * (N + (size_t)which * n + e);
     };
     uint32_t epoch = epoch_base;
 
     // publish this CTA's boundary rows (and optionally its partials); poll everyone's
-    auto exchange = [&](unsigned long long *base, T myval, T mypartial, bool with_partials, T *halo_in) {
+    auto exchange = [&](unsigned long long *base, T myval, T mypartial, bool with_partials, T *halo_in) {   // mypartial by value
         ++epoch;
-        if (with_partials && group_live && j == 0) Pkt<T>::put(part_slot(base, b), mypartial, epoch);
-        if (own_lhalo && has_left) Pkt<T>::put(row_slot(base, cta, 0, j), myval, epoch);
-        if (own_rhalo && has_right) Pkt<T>::put(row_slot(base, cta, 1, j), myval, epoch);
-        if (with_partials)
-            for (uint32_t i = t; i < N; i += bd) part[i] = Pkt<T>::get(part_slot(base, i), epoch);
-        // the left neighbour's LAST row and the right neighbour's FIRST row
-        for (uint32_t i = t; i < 2 * n; i += bd) {
-            const bool from_left = i < n;
-            const uint32_t e = from_left ? i : i - n;
-            if (from_left ? has_left : has_right)
-                halo_in[(from_left ? 0 : XS) + e] =
-                    Pkt<T>::get(row_slot(base, from_left ? cta - 1 : cta + 1, from_left ? 1 : 0, e), epoch);
+        {   // one copy of this knot row's partial per consumer CTA, spread over the lanes that hold it
+            bool sender;
+            uint32_t lanes, idx;
+            if constexpr (K::SMALL) {
+                mypartial = __shfl_sync(0xffffffffu, mypartial, 0, G);
+                sender = group_live; lanes = G; idx = j;
+            } else if constexpr (n == 64) {
+                sender = group_live && j < 32; lanes = 32; idx = j;        // knot_dot leaves the total in lanes 0..31
+            } else {
+                sender = group_live && j == 0; lanes = 1; idx = 0;
+            }
+            if (with_partials && sender)
+                for (uint32_t c = idx; c < CTAS; c += lanes) Pkt<T>::put(part_slot(base, c, b), mypartial, epoch);
+        }
+        if (own_lhalo && has_left) Pkt<T>::put(row_slot(base, cta - 1, 1, j), myval, epoch);     // I am its right neighbour
+        if (own_rhalo && has_right) Pkt<T>::put(row_slot(base, cta + 1, 0, j), myval, epoch);    // I am its left neighbour
+        constexpr uint32_t QMAX = 4, HMAX = 2;
+        if (PW == 1 && N <= QMAX * bd && 2 * n <= HMAX * bd) {
+            // one combined poll: all of this thread's packets are in flight together and re-read until every
+            // one carries this phase's epoch (a sequential spin per packet costs one L2 round trip each)
+            unsigned long long w[QMAX], wh[HMAX];
+            bool hlive[HMAX];
+#pragma unroll
+            for (uint32_t q = 0; q < HMAX; ++q) {
+                const uint32_t i = t + q * bd;
+                hlive[q] = i < 2 * n && (i < n ? has_left : has_right);
+            }
+            const unsigned long long *mine = part_slot(base, cta, 0);     // [N partials | n from left | n from right]
+            bool ok;
+            do {
+                ok = true;
+#pragma unroll
+                for (uint32_t q = 0; q < QMAX; ++q) {
+                    const uint32_t i = t + q * bd;
+                    if (with_partials && i < N) {
+                        w[q] = ld_pkt(mine + i);
+                        ok = ok && (uint32_t)(w[q] >> 32) == epoch;
+                    }
+                }
+#pragma unroll
+                for (uint32_t q = 0; q < HMAX; ++q)
+                    if (hlive[q]) {
+                        wh[q] = ld_pkt(mine + N + t + q * bd);
+                        ok = ok && (uint32_t)(wh[q] >> 32) == epoch;
+                    }
+            } while (!ok);
+#pragma unroll
+            for (uint32_t q = 0; q < QMAX; ++q) {
+                const uint32_t i = t + q * bd;
+                if (with_partials && i < N) part[i] = __uint_as_float((uint32_t)w[q]);
+            }
+#pragma unroll
+            for (uint32_t q = 0; q < HMAX; ++q) {
+                const uint32_t i = t + q * bd;
+                if (hlive[q]) halo_in[(i < n ? 0 : XS) + (i < n ? i : i - n)] = __uint_as_float((uint32_t)wh[q]);
+            }
+        } else {
+            if (with_partials)
+                for (uint32_t i = t; i < N; i += bd) part[i] = Pkt<T>::get(part_slot(base, cta, i), epoch);
+            // the left neighbour's LAST row and the right neighbour's FIRST row
+            for (uint32_t i = t; i < 2 * n; i += bd) {
+                const bool from_left = i < n;
+                const uint32_t e = from_left ? i : i - n;
+                if (from_left ? has_left : has_right)
+                    halo_in[(from_left ? 0 : XS) + e] =
+                        Pkt<T>::get(row_slot(base, cta, from_left ? 0 : 1, e), epoch);
+            }
         }
         __syncthreads();
     };
@@ -171,6 +250,18 @@ __device__ __forceinline__ uint32_t pcg_grid_body(const T *__restrict__ gS_all, 
         const T pr = mul_rn(x, y);
         if constexpr (K::SMALL) {
             return glass_tree_shfl<T, n, G>(pr, j);
+        } else if constexpr (n == 64) {
+            // two warps per knot row: the first GLASS level (i, i + 32) crosses the warps through shared memory,
+            // strides 16 .. 1 are XOR-butterfly shuffles inside the lower warp (a + b == b + a bit for bit)
+            if (is_row && j >= 32) prod[k * G + j - 32] = pr;
+            __syncthreads();
+            T x = pr;
+            if (j < 32) {
+                x = add_rn(pr, prod[k * G + j]);
+#pragma unroll
+                for (uint32_t sh = 16; sh >= 1; sh /= 2) x = add_rn(x, __shfl_xor_sync(0xffffffffu, x, sh));
+            }
+            return x;
         } else {
             if (is_row) prod[k * G + j] = pr;
             __syncthreads();

@@ -57,6 +57,9 @@ struct Shape {
     static constexpr bool FAST = fast_shape(n, N, sizeof(T));
     static constexpr uint32_t C = FAST ? N / 16 : 1;
     static constexpr uint32_t NT_FAST = 128;
+    // co-residency of all N CTAs (cooperative launch): beyond 2 x 148 CTAs the register budget must allow 4 blocks of
+    // 128 threads (= 2 of GBD_PCG_MAX_BLOCK) per SM
+    static constexpr uint32_t MIN_BLOCKS = N > 296 ? 2 : 1;
     static constexpr uint32_t G = n <= 16 ? 16 : (n <= 32 ? 32 : (n + 31) / 32 * 32);
     static constexpr uint32_t RG = (uint32_t)grid_rows(n, N, sizeof(T));
     using Fast = gbd::ClusterPcg3<FAST ? n : 2, FAST ? N : 16, FAST ? C : 1, false>;
@@ -75,7 +78,8 @@ __device__ uint32_t g_epoch;
 }  // namespace gbd_dropin
 
 template <typename T, uint32_t state_size, uint32_t knot_points>
-__global__ void __cluster_dims__(gbd_dropin::Shape<T, state_size, knot_points>::C, 1, 1) __launch_bounds__(GBD_PCG_MAX_BLOCK)
+__global__ void __cluster_dims__(gbd_dropin::Shape<T, state_size, knot_points>::C, 1, 1)
+__launch_bounds__(GBD_PCG_MAX_BLOCK, gbd_dropin::Shape<T, state_size, knot_points>::MIN_BLOCKS)
 pcg(T *d_S, T *d_Pinv, T *d_gamma, T *d_lambda, T *d_r, T *d_p, T *d_v_temp, T *d_eta_new_temp, uint32_t *d_iters,
     bool *d_max_iter_exit, uint32_t max_iter, T exit_tol)
 {

@@ -53,7 +53,9 @@ int gbd_pcg_variant_at(int i, uint32_t *n, uint32_t *N, uint32_t *cluster, int *
 /* Tuning knob: pick the cluster size (CTAs per system) and kernel build used for (n, N).
  * mode: 0 = v1 kernel, tiles in shared memory; 1 = v1, tiles in registers; 2 = v2 kernel (st.async +
  * mbarrier signalling), 1 CTA/SM register budget; 3 = v2, 2 CTAs/SM budget; 4 = grid kernel (whole GPU on
- * one system, L2 packets); 5 = v3 kernel (two matrix rows per thread), 1 CTA/SM budget; 6 = v3, 2 CTAs/SM.
+ * one system, L2 packets); 5 = v3 kernel (two matrix rows per thread), 1 CTA/SM budget; 6 = v3, 2 CTAs/SM;
+ * 7 = v4 kernel (self-validating {value, epoch} packets polled in shared memory), 1 CTA/SM; 8 = v4, 2 CTAs/SM;
+ * 9, 10 = v4 A/B and timeline builds.
  * cluster = 0 and mode = -1 restore the built-in default.  All modes give bit-identical results. */
 int gbd_pcg_set_tuning(uint32_t n, uint32_t N, int is_f64, uint32_t cluster, int mode);
 
@@ -121,6 +123,10 @@ int gbd_pcg_plan_solve_host_f64(gbd_pcg_plan *plan, const double *h_S, const dou
 
 /* Number of kernels this library has launched in this process (for bench.py's gpu_launches). */
 uint64_t gbd_pcg_launch_count(void);
+
+/* Diagnostics: device buffer that the timeline builds (mode 10) fill with per-thread %clock stamps of PCG
+ * iterations 8..11, uint32 [4][12][cluster * threads]; NULL (the default) disables it (tools/timeline.py). */
+void gbd_pcg_set_debug_buffer(void *d_buf);
 
 #ifdef __cplusplus
 }

@@ -13,6 +13,7 @@
 #include "../../include/gbd_pcg.h"
 #include "../../include/gbd/gbd_grid_pcg.cuh"
 #include "../../include/gbd/gbd_cluster_pcg_v3.cuh"
+#include "../../include/gbd/gbd_cluster_pcg_v4.cuh"
 #include <map>
 
 namespace {
@@ -23,6 +24,8 @@ using namespace gbd;
 //       2 = v2 kernel (st.async/mbarrier signalling), 1 CTA/SM register budget; 3 = v2, 2 CTAs/SM budget;
 //       4 = grid kernel (whole GPU on one system, packets through L2; C then holds the CTA count)
 //       5 = v3 kernel (two matrix rows per thread, 8-lane knot rows), 1 CTA/SM register budget; 6 = v3, 2 CTAs/SM
+//       7 = v4 kernel (self-validating packets polled in shared memory, register N-way tree), 1 CTA/SM; 8 = v4, 2 CTAs/SM
+//      10 = v4 timeline build: per-thread %clock stamps of iterations 8..11 into gbd_pcg_set_debug_buffer()
 struct Variant {
     uint32_t n, N, C;
     int mode;
@@ -57,6 +60,14 @@ Variant make_v3()
     return Variant{n, N, C, MINB == 1 ? 5 : 6, false, K::NT, K::SMEM_BYTES, (const void *)pcg_cluster_kernel_v3<n, N, C, MINB>, false, 0};
 }
 
+template <uint32_t n, uint32_t N, uint32_t C, uint32_t MINB, bool WEAK = false, bool PROF = false, uint32_t PER = 0>
+Variant make_v4()
+{
+    using K = ClusterPcg4<n, N, C, PER>;
+    return Variant{n, N, C, PROF ? 10 : (PER ? 9 : (MINB == 1 ? 7 : 8)), false, K::NT, K::SMEM_BYTES,
+                   (const void *)pcg_cluster_kernel_v4<n, N, C, MINB, WEAK, PROF, PER>, false, 0};
+}
+
 template <typename T, uint32_t n, uint32_t N, uint32_t R>
 Variant make_grid()
 {
@@ -71,8 +82,9 @@ Variant make_grid()
 std::vector<Variant> &variants()
 {
     static std::vector<Variant> v = {
-        // defaults first (measured on B200, profiles/r01_ab_bench_v3.json): v2 for single solves up to N = 256,
-        // v3 at N = 512; among the 2-CTA/SM builds (the batched default) v3 comes first
+        // defaults first (measured on B200, profiles/r01c_ab_bench.json): v4 for single solves at N = 32 / 64,
+        // v2 at N = 128 / 256, v3 at N = 512; among the 2-CTA/SM builds (the batched default) v3 comes first
+        make_v4<14, 32, 4, 1>(),                  make_v4<14, 64, 8, 1>(),
         make_v2<float, 14, 128, 16, 1>(),         make_v3<14, 128, 8, 2>(),
         make_v2<float, 14, 128, 8, 2>(),
         make_v2<float, 14, 128, 8, 1>(),          make_v2<float, 14, 128, 4, 1>(),
@@ -95,6 +107,15 @@ std::vector<Variant> &variants()
         make_v3<14, 256, 16, 1>(),                make_v3<14, 256, 8, 1>(),
         make_v3<14, 16, 2, 1>(),                  make_v3<14, 16, 1, 1>(),
         make_v3<6, 12, 3, 1>(),
+        make_v4<14, 128, 16, 1>(),                make_v4<14, 128, 8, 1>(),
+        make_v4<14, 128, 8, 2>(),                 make_v4<14, 128, 16, 2>(),
+        make_v4<14, 32, 8, 1>(),
+        make_v4<14, 32, 2, 1>(),                  make_v4<14, 32, 4, 2>(),
+        make_v4<14, 64, 4, 1>(),
+        make_v4<14, 256, 16, 1>(),                make_v4<14, 256, 8, 1>(),
+        make_v4<14, 512, 16, 1>(),
+        make_v4<14, 128, 16, 1, false, true>(),   make_v4<14, 128, 8, 1, false, true>(),
+        make_v4<14, 32, 4, 1, false, true>(),     make_v4<14, 64, 8, 1, false, true>(),
         make_variant<float, 14, 128, 8, true>(),  make_variant<float, 14, 128, 16, true>(),
         make_variant<float, 14, 128, 4, true>(),  make_variant<float, 14, 128, 8, false>(),
         make_variant<float, 14, 32, 4, true>(),   make_variant<float, 14, 32, 8, true>(),
@@ -123,6 +144,7 @@ struct Tuning { uint32_t n, N; bool f64; uint32_t C; int mode; };
 std::vector<Tuning> &tunings() { static std::vector<Tuning> t; return t; }
 std::mutex g_mu;
 std::atomic<uint64_t> g_launches{0};
+uint32_t *g_dbg = nullptr;   // timeline builds (mode 10) write %clock stamps here
 thread_local int tl_cuda_err = 0;
 
 int cuda_fail(cudaError_t e)
@@ -142,7 +164,7 @@ Variant *find_variant(uint32_t n, uint32_t N, bool f64, bool batched)
     for (auto &v : variants()) {
         if (v.n != n || v.N != N || v.f64 != f64) continue;
         if (!first) first = &v;
-        if (!first_b && (v.mode == 3 || v.mode == 6)) first_b = &v;      // 2-CTA/SM build: the default for batched launches
+        if (!first_b && (v.mode == 3 || v.mode == 6 || v.mode == 8)) first_b = &v;      // 2-CTA/SM build: the default for batched launches
         if ((wantC || wantMode >= 0) && (wantC == 0 || v.C == wantC) && (wantMode < 0 || v.mode == wantMode)) return &v;
     }
     if (wantC || wantMode >= 0) return nullptr;
@@ -252,6 +274,7 @@ int launch(uint32_t n, uint32_t N, uint32_t batch, const T *S, const T *P, const
     a.S = S; a.Pinv = P; a.gamma = g; a.lambda = lam; a.r_out = r; a.p_out = p;
     a.iters = iters; a.max_iter_exit = flag; a.batch = batch; a.max_iter = max_iter; a.exit_tol = tol;
     a.use_tma = (!no_tma && (((uintptr_t)S | (uintptr_t)P) & 15u) == 0) ? 1u : 0u;
+    a.dbg = g_dbg;
 
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute at[1];
@@ -488,6 +511,8 @@ int gbd_pcg_plan_solve_host_f64(gbd_pcg_plan *plan, const double *h_S, const dou
 {
     return plan_solve_host<double>(plan, h_S, h_Pinv, h_gamma, h_lambda, max_iter, exit_tol, h_iters, h_max_iter_exit);
 }
+
+void gbd_pcg_set_debug_buffer(void *d_buf) { g_dbg = (uint32_t *)d_buf; }
 
 uint64_t gbd_pcg_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 

@@ -16,6 +16,10 @@ from mpcgpu_b200 import _capi, synth  # noqa: E402
 from oracle import refgpu  # noqa: E402
 
 CAPS = {32: 173, 64: 167, 128: 167, 256: 118, 512: 67}
+SHAPES = [(14, 32), (14, 64), (14, 128), (14, 256), (14, 512), (64, 256)]
+if os.environ.get('AB_SHAPES'):
+    SHAPES = [tuple(int(x) for x in t.split('x')) for t in os.environ['AB_SHAPES'].split(',')]
+MODES = [int(x) for x in os.environ['AB_MODES'].split(',')] if os.environ.get('AB_MODES') else None
 
 
 def time_fn(fn, reps, warm=10):
@@ -35,9 +39,10 @@ def main():
     L = _capi.lib()
     out = []
     ring = 64
-    for (n, N) in [(14, 32), (14, 64), (14, 128), (14, 256), (14, 512)]:
+    for (n, N) in SHAPES:
         for tol in ((1e-4,) if os.environ.get('AB_QUICK') else (1e-4, 1e-6)):
-            cap = CAPS[N]
+            cap = CAPS[N] if n == 14 else 200          # config 5 (n=64, N=256): cap 200
+            ring = 64 if n == 14 else 4
             d = synth.make_systems(n, N, batch=ring, seed=77)
             S, P, g = (torch.from_numpy(d[k]).cuda() for k in ("S", "Pinv", "gamma"))
             lam = torch.zeros(ring, n * N, device="cuda")
@@ -58,7 +63,7 @@ def main():
                 lam[i].zero_()
 
             t_zero = time_fn(zero_only, 200)
-            for v in [v for v in _capi.variants() if v["n"] == n and v["N"] == N and not v["f64"]]:
+            for v in [v for v in _capi.variants() if v["n"] == n and v["N"] == N and not v["f64"] and (MODES is None or v["mode"] in MODES)]:
                 assert L.gbd_pcg_set_tuning(n, N, 0, v["cluster"], v["mode"]) == 0
                 us = time_fn(ours, 200) - t_zero
                 torch.cuda.synchronize()
@@ -67,7 +72,7 @@ def main():
                                 kernel_us=us, mean_iters=mean_it, us_per_iter=us / mean_it))
                 print(out[-1], flush=True)
                 L.gbd_pcg_set_tuning(n, N, 0, 0, -1)
-            if refgpu.available():
+            if refgpu.available() and not os.environ.get('AB_NOREF'):
                 ws = refgpu.RefWorkspace(n, N)
 
                 def ref():
@@ -106,7 +111,7 @@ def main():
             lam.zero_()
             m.solve_batched(n, N, B, S, P, g, lam, it, fl, cap, tol)
 
-        for v in [v for v in _capi.variants() if v["n"] == n and v["N"] == N and not v["f64"] and v["mode"] in (2, 3, 5, 6)]:
+        for v in [v for v in _capi.variants() if v["n"] == n and v["N"] == N and not v["f64"] and v["mode"] in (MODES or (2, 3, 5, 6, 7, 8))]:
             assert L.gbd_pcg_set_tuning(n, N, 0, v["cluster"], v["mode"]) == 0
             us = time_fn(batched, 5, warm=2)
             out.append(dict(impl="ours_batched", n=n, N=N, batch=B, cluster=v["cluster"], mode=v["mode"], ms=us / 1e3,
