@@ -106,15 +106,32 @@ struct ClusterPcg4 {
     static constexpr size_t SMEM_BYTES = OFF_P + align16(sizeof(T) * R * TILE);
 };
 
-template <uint32_t n, uint32_t N, uint32_t C, uint32_t MINB, bool WEAK = false, bool PROF = false, uint32_t PER_ = 0>
-__global__ void __launch_bounds__(ClusterPcg4<n, N, C, PER_>::NT, MINB)
-pcg_cluster_kernel_v4(const PcgArgs<float> a)
+// packet buffers cleared, tile mbarrier initialised; the caller follows it with a CTA barrier and cluster_sync()
+template <uint32_t n, uint32_t N, uint32_t C, uint32_t PER_ = 0>
+__device__ __forceinline__ void pcg_cluster_v4_init(unsigned char *smem_raw)
+{
+    using K = ClusterPcg4<n, N, C, PER_>;
+    uint64_t *pk = reinterpret_cast<uint64_t *>(smem_raw + K::OFF_PK);
+    for (uint32_t i = threadIdx.x; i < K::PK_COUNT; i += blockDim.x) pk[i] = 0ull;      // epoch 0 is never sent
+    if (threadIdx.x == 0) {
+        mbar_init(reinterpret_cast<uint64_t *>(smem_raw + K::OFF_BAR), 1);
+        fence_mbar_init();
+    }
+}
+
+// Solves systems first_sys, first_sys + sys_stride, ... < a.batch with this cluster.  Must be called by threads
+// 0 .. NT-1 of every CTA of the cluster (and only by them: the intra-CTA barriers are named barriers over NT
+// threads, so a launch may carry idle extra threads -- the drop-in pcg<T,n,N> runs under the caller's block size).
+template <uint32_t n, uint32_t N, uint32_t C, bool WEAK = false, bool PROF = false, uint32_t PER_ = 0, bool EXACT_BLOCK = false>
+__device__ __forceinline__ void pcg_cluster_v4_run(const PcgArgs<float> &a, unsigned char *smem_raw, uint32_t first_sys,
+                                                   uint32_t sys_stride)
 {
     using K = ClusterPcg4<n, N, C, PER_>;
     using T = float;
     constexpr uint32_t R = K::R, W = K::W, TILE = K::TILE, G = K::G, XS = K::XS, NT = K::NT, PER = K::PER, LW = K::LW;
+    // EXACT_BLOCK: the launch carries exactly NT threads, so the plain CTA barrier (cheaper than a counted one) is safe
+    auto cta_sync = [&]() { if constexpr (EXACT_BLOCK) __syncthreads(); else named_bar_sync(2, NT); };
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t *barT = reinterpret_cast<uint64_t *>(smem_raw + K::OFF_BAR);
     uint64_t *pk = reinterpret_cast<uint64_t *>(smem_raw + K::OFF_PK);
     T *xp = reinterpret_cast<T *>(smem_raw + K::OFF_XP);   // p (prologue: lambda) rows, one halo row each side
@@ -128,7 +145,6 @@ pcg_cluster_kernel_v4(const PcgArgs<float> a)
     const bool is_row = j < n;
     const uint32_t jn = is_row ? j : 0;
     const uint32_t cr = cluster_ctarank();
-    const uint32_t cid = cluster_idx(), ncl = cluster_count();
     const uint32_t b = cr * R + k;
     const bool has_left = cr > 0, has_right = cr + 1 < C;
     // halo duty: group 0 keeps the copy of the left neighbour's last row, group R-1 of the right one's first
@@ -188,16 +204,8 @@ pcg_cluster_kernel_v4(const PcgArgs<float> a)
         return x;
     };
 
-    for (uint32_t i = t; i < K::PK_COUNT; i += NT) pk[i] = 0ull;      // epoch 0 is never sent
-    if (t == 0) {
-        mbar_init(barT, 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-    cluster_sync();   // all CTAs resident, packet buffers cleared, before any DSMEM traffic
-
     uint32_t phT = 0, ep = 0;
-    for (uint32_t sys = cid; sys < a.batch; sys += ncl) {
+    for (uint32_t sys = first_sys; sys < a.batch; sys += sys_stride) {
         const size_t moff = ((size_t)sys * N + (size_t)cr * R) * TILE;
         const size_t vbase = (size_t)sys * N * n;
         const T *gS = a.S + moff, *gP = a.Pinv + moff;
@@ -233,7 +241,7 @@ pcg_cluster_kernel_v4(const PcgArgs<float> a)
         }
         if (tma) mbar_wait(barT, phT);
         phT ^= 1u;
-        __syncthreads();
+        cta_sync();
 
         // this thread's rows of S and Pinv live in registers for the whole solve; the tiles the reference
         // never reads (left of block row 0, right of block row N-1) are taken as zero
@@ -263,7 +271,7 @@ pcg_cluster_kernel_v4(const PcgArgs<float> a)
             *halo_xr = packet_val(hq);
         }
         T rh = halo ? *halo_xr : T(0);                      // register copy of the neighbour's boundary r element
-        __syncthreads();
+        cta_sync();
         // ---- r~ = Pinv*r ; p = r~ ; eta = r.r~                             (pcg.cuh:130-149)
         T rt = chain_padded<T, n, XS>(mp, wr);
         ++ep;
@@ -293,7 +301,7 @@ pcg_cluster_kernel_v4(const PcgArgs<float> a)
             }
         };
         for (; iter < a.max_iter; ++iter) {
-            __syncthreads();
+            cta_sync();
             stamp(0, p);
             // ---- upsilon = S*p ; v = p.upsilon                             (pcg.cuh:156-167)
             ups = chain_padded<T, n, XS>(ms, wp);
@@ -310,7 +318,7 @@ pcg_cluster_kernel_v4(const PcgArgs<float> a)
             r = fma_rn(-alpha, ups, r);
             if (is_row) *own_r = r;
             if (halo) { rh = fma_rn(-alpha, edge, rh); *halo_xr = rh; }
-            __syncthreads();
+            cta_sync();
             stamp(5, r);
             // ---- r~ = Pinv*r ; eta' = r.r~                                 (:180-193)
             rt = chain_padded<T, n, XS>(mp, wr);
@@ -343,8 +351,20 @@ pcg_cluster_kernel_v4(const PcgArgs<float> a)
             a.iters[sys] = iter;
             a.max_iter_exit[sys] = max_iter_exit;
         }
-        __syncthreads();
+        cta_sync();
     }
+}
+
+// C-ABI kernel: persistent clusters looping over a batch of systems
+template <uint32_t n, uint32_t N, uint32_t C, uint32_t MINB, bool WEAK = false, bool PROF = false, uint32_t PER_ = 0>
+__global__ void __launch_bounds__(ClusterPcg4<n, N, C, PER_>::NT, MINB)
+pcg_cluster_kernel_v4(const PcgArgs<float> a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    pcg_cluster_v4_init<n, N, C, PER_>(smem_raw);
+    __syncthreads();
+    cluster_sync();   // all CTAs resident, packet buffers cleared, before any DSMEM traffic
+    pcg_cluster_v4_run<n, N, C, WEAK, PROF, PER_, true>(a, smem_raw, cluster_idx(), cluster_count());
     cluster_sync();   // no CTA leaves while a peer may still write into its shared memory
 }
 

@@ -14,6 +14,7 @@
 #include "utils.cuh"
 #include "gbd/gbd_grid_pcg.cuh"
 #include "gbd/gbd_cluster_pcg_v3.cuh"
+#include "gbd/gbd_cluster_pcg_v4.cuh"
 
 #ifndef GBD_PCG_MAX_BLOCK
 #define GBD_PCG_MAX_BLOCK 256           // upper bound on the caller's block size (register budget of pcg<>)
@@ -33,29 +34,46 @@ constexpr size_t fast_smem(size_t n, size_t N)
     const size_t xs = (n + 3) / 4 * 4;
     return 32 + 2 * a16(4 * 18 * xs) + 3 * a16(4 * 2 * xs) + 2 * a16(4 * N);
 }
+// v4 (packet) body: fp32, n <= 16, N = 32 or 64 -> clusters of N/8 CTAs x 128 threads (8 knot rows per CTA)
+constexpr bool fast4_shape(size_t n, size_t N, size_t e)
+{
+#ifdef GBD_DROPIN_NO_CLUSTER
+    return false;
+#else
+    return e == 4 && n >= 2 && n <= 16 && (N == 32 || N == 64);
+#endif
+}
+constexpr size_t fast4_smem(size_t n, size_t N)
+{
+    const size_t xs = (n + 3) / 4 * 4;
+    return 16 + 8 * (3 * N + 8 * xs) + 2 * a16(4 * 10 * xs) + 2 * a16(4 * 8 * 3 * n * n);
+}
 constexpr bool fast_shape(size_t n, size_t N, size_t e)
 {
 #ifdef GBD_DROPIN_NO_CLUSTER
     return false;
 #else
-    return e == 4 && n % 2 == 0 && n <= 16 && N % 16 == 0 && N / 16 <= 8;
+    return e == 4 && n % 2 == 0 && n <= 16 && N % 16 == 0 && N / 16 <= 8 && !fast4_shape(n, N, e);
 #endif
 }
 constexpr size_t grid_rows(size_t n, size_t N, size_t e)     // knot rows per CTA of the packet kernel when the block allows
 {
-    return (!fast_shape(n, N, e) && N % 8 == 0 && N / 8 >= 2 && 8 * lanes_per_row(n) <= GBD_PCG_MAX_BLOCK &&
+    return (!fast_shape(n, N, e) && !fast4_shape(n, N, e) && N % 8 == 0 && N / 8 >= 2 && 8 * lanes_per_row(n) <= GBD_PCG_MAX_BLOCK &&
             grid_smem(n, N, 8, e) <= 48 * 1024) ? 8 : 1;
 }
 // How pcg<T,n,N> is carried out under the reference's launch (cooperative, grid = N CTAs, caller's block size):
 //   FAST  fp32, even n <= 16, N a multiple of 16 with N/16 <= 8 (IIWA: N = 16 .. 128), block >= 128 threads:
 //         the kernel carries compile-time cluster dimensions C = N/16; cluster 0 of the grid runs the
 //         cluster-resident solver (gbd_cluster_pcg_v3.cuh, DSMEM + mbarrier exchange), all other CTAs return.
+//   FAST4 fp32, n <= 16, N = 32 / 64, block >= 128 threads: same scheme with clusters of N/8 CTAs running the packet
+//         solver (gbd_cluster_pcg_v4.cuh: {value, epoch} packets polled in shared memory, tiles staged by TMA).
 //   GRID  everything else: one CTA per RG knot rows exchanges through L2 packets (gbd_grid_pcg.cuh);
 //         RG = 8 when the block has >= 8 row groups of threads, else 1.  CTAs beyond N/RG return.
 template <typename T, uint32_t n, uint32_t N>
 struct Shape {
     static constexpr bool FAST = fast_shape(n, N, sizeof(T));
-    static constexpr uint32_t C = FAST ? N / 16 : 1;
+    static constexpr bool FAST4 = fast4_shape(n, N, sizeof(T));
+    static constexpr uint32_t C = FAST4 ? N / 8 : (FAST ? N / 16 : 1);
     static constexpr uint32_t NT_FAST = 128;
     // co-residency of all N CTAs (cooperative launch): beyond 2 x 148 CTAs the register budget must allow 4 blocks of
     // 128 threads (= 2 of GBD_PCG_MAX_BLOCK) per SM
@@ -63,7 +81,9 @@ struct Shape {
     static constexpr uint32_t G = n <= 16 ? 16 : (n <= 32 ? 32 : (n + 31) / 32 * 32);
     static constexpr uint32_t RG = (uint32_t)grid_rows(n, N, sizeof(T));
     using Fast = gbd::ClusterPcg3<FAST ? n : 2, FAST ? N : 16, FAST ? C : 1, false>;
-    static constexpr size_t SMEM_FAST = FAST ? Fast::SMEM_BYTES : 0;
+    using Fast4 = gbd::ClusterPcg4<FAST4 ? n : 2, FAST4 ? N : 32, FAST4 ? C : 4>;
+    static_assert(!FAST4 || (Fast4::SMEM_BYTES == fast4_smem(n, N) && Fast4::NT == 128), "run-time smem formula out of sync");
+    static constexpr size_t SMEM_FAST = FAST4 ? Fast4::SMEM_BYTES : (FAST ? Fast::SMEM_BYTES : 0);
     static_assert(!FAST || Fast::SMEM_BYTES == fast_smem(n, N), "run-time smem formula out of sync");
     static_assert(gbd::GridPcg<T, n, N, 1>::SMEM_BYTES == grid_smem(n, N, 1, sizeof(T)), "run-time smem formula out of sync");
     static constexpr size_t SMEM_G1 = gbd::GridPcg<T, n, N, 1>::SMEM_BYTES;
@@ -87,6 +107,19 @@ pcg(T *d_S, T *d_Pinv, T *d_gamma, T *d_lambda, T *d_r, T *d_p, T *d_v_temp, T *
     extern __shared__ __align__(16) unsigned char gbd_dropin_smem[];
     (void)d_v_temp; (void)d_eta_new_temp;          // reference scratch for its smem trees; not needed here
     uint8_t *d_flag = reinterpret_cast<uint8_t *>(d_max_iter_exit);
+    if constexpr (SH::FAST4) {
+        if (blockDim.x >= SH::NT_FAST) {
+            if (gbd::cluster_idx() != 0) return;                  // whole clusters leave together
+            const uint32_t tma4 = ((((uintptr_t)d_S) | ((uintptr_t)d_Pinv)) & 15u) == 0 ? 1u : 0u;
+            gbd::PcgArgs<float> a{d_S, d_Pinv, d_gamma, d_lambda, d_r, d_p, d_iters, d_flag, 1u, max_iter, exit_tol, tma4};
+            gbd::pcg_cluster_v4_init<state_size, knot_points, SH::C>(gbd_dropin_smem);
+            __syncthreads();
+            gbd::cluster_sync();
+            if (threadIdx.x < SH::NT_FAST) gbd::pcg_cluster_v4_run<state_size, knot_points, SH::C>(a, gbd_dropin_smem, 0u, 1u);
+            gbd::cluster_sync();
+            return;
+        }
+    }
     if constexpr (SH::FAST) {
         if (blockDim.x >= SH::NT_FAST) {
             if (gbd::cluster_idx() != 0) return;                  // whole clusters leave together
@@ -123,6 +156,7 @@ size_t pcgSharedMemSize(uint32_t state_size, uint32_t knot_points)
     const size_t n = state_size, N = knot_points, e = sizeof(T);
     size_t need = gbd_dropin::grid_smem(n, N, 1, e);
     if (gbd_dropin::fast_shape(n, N, e) && gbd_dropin::fast_smem(n, N) > need) need = gbd_dropin::fast_smem(n, N);
+    if (gbd_dropin::fast4_shape(n, N, e) && gbd_dropin::fast4_smem(n, N) > need) need = gbd_dropin::fast4_smem(n, N);
     const size_t rg = gbd_dropin::grid_rows(n, N, e);
     if (rg > 1 && gbd_dropin::grid_smem(n, N, rg, e) > need) need = gbd_dropin::grid_smem(n, N, rg, e);
     return need;

@@ -307,7 +307,8 @@ def test_dropin_headers_on_golden_reference_vectors(torch_cuda, tmp_path, knots,
             _assert_same(got, run, f"drop-in {g['name']} block={block} tol={run['tol']}")
 
 
-@pytest.mark.parametrize("knots,block", [(32, 128), (32, 64), (128, 128), (128, 64), (32, 256), (256, 128), (512, 128), (512, 64)])
+@pytest.mark.parametrize("knots,block", [(32, 128), (32, 64), (64, 128), (64, 256), (64, 64), (128, 128), (128, 64), (32, 256), (256, 128),
+                                         (512, 128), (512, 64)])
 def test_dropin_headers_reference_launch_geometry(torch_cuda, oracle_pcg, tmp_path, knots, block):
     """include/gbd_dropin: pcg<float,14,N> launched exactly like include/pcg/sqp.cuh:230 (cooperative,
     grid = N, block = PCG_NUM_THREADS, smem = pcgSharedMemSize) -- bit-exact vs the oracle."""
