@@ -15,6 +15,7 @@
 #include "gbd/gbd_grid_pcg.cuh"
 #include "gbd/gbd_cluster_pcg_v3.cuh"
 #include "gbd/gbd_cluster_pcg_v4.cuh"
+#include "gbd/gbd_cluster_pcg_v5.cuh"
 
 #ifndef GBD_PCG_MAX_BLOCK
 #define GBD_PCG_MAX_BLOCK 256           // upper bound on the caller's block size (register budget of pcg<>)
@@ -33,6 +34,13 @@ constexpr size_t fast_smem(size_t n, size_t N)
 {
     const size_t xs = (n + 3) / 4 * 4;
     return 32 + 2 * a16(4 * 18 * xs) + 3 * a16(4 * 2 * xs) + 2 * a16(4 * N);
+}
+// v5 body (v3's mapping + packet exchange, tiles loaded straight from global): the FAST shapes with a power-of-two N >= 32
+constexpr bool fast5_shape(size_t N) { return N >= 32 && (N & (N - 1)) == 0; }
+constexpr size_t fast5_smem(size_t n, size_t N)
+{
+    const size_t xs = (n + 3) / 4 * 4;
+    return 16 + 8 * (3 * N + 8 * xs) + 2 * a16(4 * 18 * xs);
 }
 // v4 (packet) body: fp32, n <= 16, N = 32 or 64 -> clusters of N/8 CTAs x 128 threads (8 knot rows per CTA)
 constexpr bool fast4_shape(size_t n, size_t N, size_t e)
@@ -65,6 +73,7 @@ constexpr size_t grid_rows(size_t n, size_t N, size_t e)     // knot rows per CT
 //   FAST  fp32, even n <= 16, N a multiple of 16 with N/16 <= 8 (IIWA: N = 16 .. 128), block >= 128 threads:
 //         the kernel carries compile-time cluster dimensions C = N/16; cluster 0 of the grid runs the
 //         cluster-resident solver (gbd_cluster_pcg_v3.cuh, DSMEM + mbarrier exchange), all other CTAs return.
+//         (power-of-two N >= 32, i.e. N = 128 for IIWA: the packet-exchange body gbd_cluster_pcg_v5.cuh instead.)
 //   FAST4 fp32, n <= 16, N = 32 / 64, block >= 128 threads: same scheme with clusters of N/8 CTAs running the packet
 //         solver (gbd_cluster_pcg_v4.cuh: {value, epoch} packets polled in shared memory, tiles staged by TMA).
 //   GRID  everything else: one CTA per RG knot rows exchanges through L2 packets (gbd_grid_pcg.cuh);
@@ -81,9 +90,12 @@ struct Shape {
     static constexpr uint32_t G = n <= 16 ? 16 : (n <= 32 ? 32 : (n + 31) / 32 * 32);
     static constexpr uint32_t RG = (uint32_t)grid_rows(n, N, sizeof(T));
     using Fast = gbd::ClusterPcg3<FAST ? n : 2, FAST ? N : 16, FAST ? C : 1, false>;
+    static constexpr bool FAST5 = FAST && fast5_shape(N);
+    using Fast5 = gbd::ClusterPcg5<FAST5 ? n : 2, FAST5 ? N : 32, FAST5 ? C : 2, false>;
+    static_assert(!FAST5 || (Fast5::SMEM_BYTES == fast5_smem(n, N) && Fast5::NT == 128), "run-time smem formula out of sync");
     using Fast4 = gbd::ClusterPcg4<FAST4 ? n : 2, FAST4 ? N : 32, FAST4 ? C : 4>;
     static_assert(!FAST4 || (Fast4::SMEM_BYTES == fast4_smem(n, N) && Fast4::NT == 128), "run-time smem formula out of sync");
-    static constexpr size_t SMEM_FAST = FAST4 ? Fast4::SMEM_BYTES : (FAST ? Fast::SMEM_BYTES : 0);
+    static constexpr size_t SMEM_FAST = FAST4 ? Fast4::SMEM_BYTES : (FAST5 ? Fast5::SMEM_BYTES : (FAST ? Fast::SMEM_BYTES : 0));
     static_assert(!FAST || Fast::SMEM_BYTES == fast_smem(n, N), "run-time smem formula out of sync");
     static_assert(gbd::GridPcg<T, n, N, 1>::SMEM_BYTES == grid_smem(n, N, 1, sizeof(T)), "run-time smem formula out of sync");
     static constexpr size_t SMEM_G1 = gbd::GridPcg<T, n, N, 1>::SMEM_BYTES;
@@ -124,6 +136,15 @@ pcg(T *d_S, T *d_Pinv, T *d_gamma, T *d_lambda, T *d_r, T *d_p, T *d_v_temp, T *
         if (blockDim.x >= SH::NT_FAST) {
             if (gbd::cluster_idx() != 0) return;                  // whole clusters leave together
             gbd::PcgArgs<float> a{d_S, d_Pinv, d_gamma, d_lambda, d_r, d_p, d_iters, d_flag, 1u, max_iter, exit_tol, 0u};
+            if constexpr (SH::FAST5) {
+                gbd::pcg_cluster_v5_init<state_size, knot_points, SH::C, false>(gbd_dropin_smem);
+                __syncthreads();
+                gbd::cluster_sync();
+                if (threadIdx.x < SH::NT_FAST)
+                    gbd::pcg_cluster_v5_run<state_size, knot_points, SH::C, false, false>(a, gbd_dropin_smem, 0u, 1u);
+                gbd::cluster_sync();
+                return;
+            }
             gbd::pcg_cluster_v3_init<state_size, knot_points, SH::C, false>(gbd_dropin_smem);
             __syncthreads();
             gbd::cluster_sync();
@@ -157,6 +178,7 @@ size_t pcgSharedMemSize(uint32_t state_size, uint32_t knot_points)
     size_t need = gbd_dropin::grid_smem(n, N, 1, e);
     if (gbd_dropin::fast_shape(n, N, e) && gbd_dropin::fast_smem(n, N) > need) need = gbd_dropin::fast_smem(n, N);
     if (gbd_dropin::fast4_shape(n, N, e) && gbd_dropin::fast4_smem(n, N) > need) need = gbd_dropin::fast4_smem(n, N);
+    if (gbd_dropin::fast_shape(n, N, e) && gbd_dropin::fast5_shape(N) && gbd_dropin::fast5_smem(n, N) > need) need = gbd_dropin::fast5_smem(n, N);
     const size_t rg = gbd_dropin::grid_rows(n, N, e);
     if (rg > 1 && gbd_dropin::grid_smem(n, N, rg, e) > need) need = gbd_dropin::grid_smem(n, N, rg, e);
     return need;

@@ -14,6 +14,7 @@
 #include "../../include/gbd/gbd_grid_pcg.cuh"
 #include "../../include/gbd/gbd_cluster_pcg_v3.cuh"
 #include "../../include/gbd/gbd_cluster_pcg_v4.cuh"
+#include "../../include/gbd/gbd_cluster_pcg_v5.cuh"
 #include <map>
 
 namespace {
@@ -25,6 +26,7 @@ using namespace gbd;
 //       4 = grid kernel (whole GPU on one system, packets through L2; C then holds the CTA count)
 //       5 = v3 kernel (two matrix rows per thread, 8-lane knot rows), 1 CTA/SM register budget; 6 = v3, 2 CTAs/SM
 //       7 = v4 kernel (self-validating packets polled in shared memory, register N-way tree), 1 CTA/SM; 8 = v4, 2 CTAs/SM
+//      11 = v5 kernel (v3's two-rows-per-thread mapping + v4's packet exchange), 1 CTA/SM; 12 = v5, 2 CTAs/SM
 //      10 = v4 timeline build: per-thread %clock stamps of iterations 8..11 into gbd_pcg_set_debug_buffer()
 struct Variant {
     uint32_t n, N, C;
@@ -66,6 +68,13 @@ Variant make_v4()
     using K = ClusterPcg4<n, N, C, PER>;
     return Variant{n, N, C, PROF ? 10 : (PER ? 9 : (MINB == 1 ? 7 : 8)), false, K::NT, K::SMEM_BYTES,
                    (const void *)pcg_cluster_kernel_v4<n, N, C, MINB, WEAK, PROF, PER>, false, 0};
+}
+
+template <uint32_t n, uint32_t N, uint32_t C, uint32_t MINB>
+Variant make_v5()
+{
+    using K = ClusterPcg5<n, N, C, true>;
+    return Variant{n, N, C, MINB == 1 ? 11 : 12, false, K::NT, K::SMEM_BYTES, (const void *)pcg_cluster_kernel_v5<n, N, C, MINB>, false, 0};
 }
 
 template <typename T, uint32_t n, uint32_t N, uint32_t R>
@@ -114,6 +123,10 @@ std::vector<Variant> &variants()
         make_v4<14, 64, 4, 1>(),
         make_v4<14, 256, 16, 1>(),                make_v4<14, 256, 8, 1>(),
         make_v4<14, 512, 16, 1>(),
+        make_v5<14, 128, 8, 1>(),                 make_v5<14, 128, 8, 2>(),
+        make_v5<14, 128, 4, 1>(),                 make_v5<14, 64, 4, 1>(),
+        make_v5<14, 64, 8, 1>(),                  make_v5<14, 32, 2, 1>(),
+        make_v5<14, 32, 4, 1>(),                  make_v5<14, 256, 8, 1>(),
         make_v4<14, 128, 16, 1, false, true>(),   make_v4<14, 128, 8, 1, false, true>(),
         make_v4<14, 32, 4, 1, false, true>(),     make_v4<14, 64, 8, 1, false, true>(),
         make_variant<float, 14, 128, 8, true>(),  make_variant<float, 14, 128, 16, true>(),
@@ -164,10 +177,18 @@ Variant *find_variant(uint32_t n, uint32_t N, bool f64, bool batched)
     for (auto &v : variants()) {
         if (v.n != n || v.N != N || v.f64 != f64) continue;
         if (!first) first = &v;
-        if (!first_b && (v.mode == 3 || v.mode == 6 || v.mode == 8)) first_b = &v;      // 2-CTA/SM build: the default for batched launches
+        if (!first_b && (v.mode == 3 || v.mode == 6 || v.mode == 8 || v.mode == 12)) first_b = &v;      // 2-CTA/SM build: the default for batched launches
         if ((wantC || wantMode >= 0) && (wantC == 0 || v.C == wantC) && (wantMode < 0 || v.mode == wantMode)) return &v;
     }
     if (wantC || wantMode >= 0) return nullptr;
+    if (batched) {
+        // measured batched defaults (profiles/r01c_ab_bench.json): v5 with 4 CTAs per system at N = 128, 2 at N = 32
+        static const Tuning batched_defaults[] = {{14, 128, false, 4, 11}, {14, 32, false, 2, 11}};
+        for (auto &t : batched_defaults)
+            if (t.n == n && t.N == N && t.f64 == f64)
+                for (auto &v : variants())
+                    if (v.n == n && v.N == N && v.f64 == f64 && v.C == t.C && v.mode == t.mode) return &v;
+    }
     return (batched && first_b) ? first_b : first;
 }
 
