@@ -1,0 +1,289 @@
+// gbd_schur.cuh -- the two steps either side of the PCG solve inside one SQP iteration:
+//
+//   form_schur   replaces form_schur_system<T>  (include/pcg/linsys_setup.cuh:621-657: cooperative kernel
+//                form_S_gamma_Pinv_kernel = form_S_gamma_and_jacobi_Pinv_blockrow :139-562, grid.sync,
+//                complete_SS_Pinv_blockrow :9-137): KKT blocks (G, C, g, c) -> S, Pinv, gamma in the pcg<> layout,
+//                G overwritten with the block inverses that compute_dz needs
+//   compute_dz   replaces compute_dz<T>          (include/common/dz.cuh:3-136)
+//
+// Same inputs, outputs, layouts and the same floating-point operation ORDER as the reference (every dot product is
+// one FMA per term in ascending index order, the Gauss-Jordan updates are x/piv and fma(-(c/piv), r, x) resp.
+// x*pvInv and fma(-(c*pvInv), r, x), IEEE division), so the results are bit-identical to the reference kernels
+// (asserted against oracle/_ref/libref_schur.so and the C oracle).  What differs is the machine mapping:
+//
+//   reference                                       here
+//   ---------                                       ----
+//   one cooperative launch, grid.sync between the   two ordinary launches (stream order is the dependency); no
+//   two phases (all N CTAs must be co-resident)     co-residency requirement, so any N and batches work
+//   ~60 __syncthreads per block row: every step of  5 CTA barriers per block row: the three Gauss-Jordan inversions
+//   every 14-pivot inversion is a CTA barrier pair  run concurrently in three warps on __syncwarp; independent
+//                                                   products (A Q^-1, B R^-1, Q^-1 q ...) share a stage
+//   per-element division in the pivot update        one division per row and pivot (same operands -> same bits)
+//   CTA k overwrites G slot k-1 with the inverse    inverses are parked in Pinv tiles that phase 2 overwrites
+//   while CTA k-1 may still read it (a race that    anyway (left tile of row k, right tile of row k-1, the pad
+//   only co-residency hides)                        tile of row 0) and moved into G by the phase-2 CTA that owns
+//                                                   the tile: in place like the reference, race-free
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace gbd {
+
+namespace schur_detail {
+
+__device__ __forceinline__ float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+
+// Gauss-Jordan on [V | I] (DIM x 2 DIM, column-major) by ONE warp, the reference's several-matrices-at-once
+// arithmetic (matrix.cuh:149-238): per pivot p and for the DIM+1 columns p .. p+DIM,
+//   row == p : x /= piv         else : x = fma(-(col[row] / piv), rowv[col], x)
+template <uint32_t DIM>
+__device__ __forceinline__ void gj_div_warp(float *A, float *snap, uint32_t lane)
+{
+    float *colv = snap, *rowv = snap + DIM, *f = snap + 2 * DIM + 1;
+    for (uint32_t p = 0; p < DIM; ++p) {
+        const uint32_t off = p * DIM;
+        for (uint32_t i = lane; i < DIM; i += 32) colv[i] = A[i + off];
+        for (uint32_t i = lane; i < DIM + 1; i += 32) rowv[i] = A[i * DIM + p + off];
+        __syncwarp();
+        const float piv = colv[p];
+        for (uint32_t i = lane; i < DIM; i += 32) f[i] = __fdiv_rn(colv[i], piv);
+        __syncwarp();
+        for (uint32_t ind = lane; ind < DIM * (DIM + 1); ind += 32) {
+            const uint32_t row = ind % DIM, col = ind / DIM;
+            const float x = A[off + ind];
+            A[off + ind] = (row == p) ? __fdiv_rn(x, piv) : fma_(-f[row], rowv[col], x);
+        }
+        __syncwarp();
+    }
+}
+
+// the reference's single-matrix arithmetic (matrix.cuh:120-146): pvInv = 1 / piv,
+//   row == p : x *= pvInv       else : x = fma(-(col[row] * pvInv), rowv[col], x)
+template <uint32_t DIM>
+__device__ __forceinline__ void gj_rcp_warp(float *A, float *snap, uint32_t lane)
+{
+    float *colv = snap, *rowv = snap + DIM, *f = snap + 2 * DIM + 1;
+    for (uint32_t p = 0; p < DIM; ++p) {
+        const uint32_t off = p * DIM;
+        for (uint32_t i = lane; i < DIM; i += 32) colv[i] = A[i + off];
+        for (uint32_t i = lane; i < DIM + 1; i += 32) rowv[i] = A[i * DIM + p + off];
+        __syncwarp();
+        const float pv_inv = __fdiv_rn(1.0f, colv[p]);
+        for (uint32_t i = lane; i < DIM; i += 32) f[i] = __fmul_rn(colv[i], pv_inv);
+        __syncwarp();
+        for (uint32_t ind = lane; ind < DIM * (DIM + 1); ind += 32) {
+            const uint32_t row = ind % DIM, col = ind / DIM;
+            const float x = A[off + ind];
+            A[off + ind] = (row == p) ? __fmul_rn(x, pv_inv) : fma_(-f[row], rowv[col], x);
+        }
+        __syncwarp();
+    }
+}
+
+// one element of C (M x NC) = A (M x K) * B (K x NC)  [TB: A * B^T with B stored NC x K], column-major,
+// one FMA per term in ascending k (GLASS/src/L3/gemm.cuh:47-96)
+template <bool TB>
+__device__ __forceinline__ float gemm_elem(const float *A, const float *B, uint32_t M, uint32_t K, uint32_t NC, uint32_t row,
+                                           uint32_t col)
+{
+    float res = 0.0f;
+    for (uint32_t k = 0; k < K; ++k) res = fma_(A[k * M + row], TB ? B[k * NC + col] : B[col * K + k], res);
+    return res;
+}
+// one element of mat (ROWS x COLS, column-major) * vec  (matrix.cuh:42-54)
+__device__ __forceinline__ float matvec_elem(const float *mat, const float *vec, uint32_t ROWS, uint32_t COLS, uint32_t row)
+{
+    float res = 0.0f;
+    for (uint32_t c = 0; c < COLS; ++c) res = fma_(mat[row + c * ROWS], vec[c], res);
+    return res;
+}
+__device__ __forceinline__ void identity(float *A, uint32_t dim, uint32_t t, uint32_t nt)
+{
+    for (uint32_t i = t; i < dim * dim; i += nt) A[i] = (i % dim == i / dim) ? 1.0f : 0.0f;
+}
+
+}  // namespace schur_detail
+
+template <uint32_t n, uint32_t m>
+struct SchurShape {
+    static constexpr uint32_t NT = 128;
+    static constexpr uint32_t nn = n * n, mm = m * m, nm = n * m;
+    static constexpr uint32_t GSET = nn + mm, CSET = nn + nm;
+    // phase-1 shared memory (floats)
+    static constexpr uint32_t P1_FLOATS = nn /*A*/ + nm /*B*/ + 2 * nn /*Qk|I*/ + 2 * nn /*Qkp1|I*/ + 2 * mm /*R|I*/ + nn /*phi*/ + nm /*BR*/ +
+                                          2 * nn /*theta|I*/ + nn /*BRBt*/ + 6 * n + m + 3 * (3 * n + 2);
+    static constexpr uint32_t P2_FLOATS = 7 * nn;
+};
+
+// ---- phase 1: one CTA per block row (linsys_setup.cuh:139-562)
+template <uint32_t n, uint32_t m>
+__global__ void __launch_bounds__(SchurShape<n, m>::NT)
+schur_phase1_kernel(uint32_t N, const float *__restrict__ G, const float *__restrict__ C, const float *__restrict__ g,
+                    const float *__restrict__ c, float *__restrict__ S, float *__restrict__ Pinv, float *__restrict__ gamma, float rho)
+{
+    using namespace schur_detail;
+    using K = SchurShape<n, m>;
+    constexpr uint32_t nn = K::nn, mm = K::mm, nm = K::nm, NT = K::NT;
+    extern __shared__ float sm[];
+    float *sA = sm, *sB = sA + nn, *sQk = sB + nm, *sQk_i = sQk + nn, *sQp = sQk_i + nn, *sQp_i = sQp + nn;
+    float *sR = sQp_i + nn, *sR_i = sR + mm, *sPhi = sR_i + mm, *sBR = sPhi + nn, *sTh = sBR + nm, *sTh_i = sTh + nn;
+    float *sBRBt = sTh_i + nn, *sqk = sBRBt + nn, *sqp = sqk + n, *srk = sqp + n, *sgam = srk + m, *sx0 = sgam + n, *sx1 = sx0 + n;
+    float *sc = sx1 + n, *snap = sc + n;                      // 3 snapshots of 3n+2 floats
+    const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5, b = blockIdx.x;
+    float *Srow = S + (size_t)b * 3 * nn, *Prow = Pinv + (size_t)b * 3 * nn;
+
+    if (b == 0) {
+        // ---- leading block (:151-278): Pinv_00 = -(Q_0 + rho I), S_00 = -Q_0^-1, gamma_0 = -Q_0^-1 q_0
+        for (uint32_t i = t; i < nn; i += NT) sQk[i] = (i % n == i / n) ? __fadd_rn(G[i], rho) : G[i];
+        identity(sQk_i, n, t, NT);
+        for (uint32_t i = t; i < n; i += NT) sqk[i] = g[i];
+        __syncthreads();
+        for (uint32_t i = t; i < nn; i += NT) Prow[nn + i] = sQk[i] * -1.0f;
+        __syncthreads();
+        if (warp == 0) gj_div_warp<n>(sQk, snap, lane);
+        __syncthreads();
+        for (uint32_t i = t; i < nn; i += NT) Srow[nn + i] = sQk_i[i] * -1.0f;
+        for (uint32_t i = t; i < n; i += NT) gamma[i] = -matvec_elem(sQk_i, sqk, n, n, i);
+        return;
+    }
+    // ---- block rows 1 .. N-1 (:280-560); the reference's "k" blocks are knot b-1, its "kp1" blocks knot b
+    const float *Gk = G + (size_t)(b - 1) * K::GSET, *Gp = G + (size_t)b * K::GSET, *Ck = C + (size_t)(b - 1) * K::CSET;
+    for (uint32_t i = t; i < nn; i += NT) {
+        const bool diag = i % n == i / n;
+        sA[i] = Ck[i];
+        sQk[i] = diag ? __fadd_rn(Gk[i], rho) : Gk[i];
+        sQp[i] = diag ? __fadd_rn(Gp[i], rho) : Gp[i];
+    }
+    for (uint32_t i = t; i < nm; i += NT) sB[i] = Ck[nn + i];
+    for (uint32_t i = t; i < mm; i += NT) sR[i] = (i % m == i / m) ? __fadd_rn(Gk[nn + i], rho) : Gk[nn + i];
+    for (uint32_t i = t; i < n; i += NT) {
+        sqk[i] = g[(size_t)(b - 1) * (n + m) + i];
+        sqp[i] = g[(size_t)b * (n + m) + i];
+        sc[i] = c[(size_t)b * n + i];
+    }
+    for (uint32_t i = t; i < m; i += NT) srk[i] = g[(size_t)(b - 1) * (n + m) + n + i];
+    identity(sQk_i, n, t, NT);
+    identity(sQp_i, n, t, NT);
+    identity(sR_i, m, t, NT);
+    __syncthreads();
+    // ---- the three inversions side by side, one warp each (:351-363)
+    if (warp == 0) gj_div_warp<n>(sQk, snap, lane);
+    else if (warp == 1) gj_div_warp<n>(sQp, snap + (3 * n + 2), lane);
+    else if (warp == 2) gj_div_warp<m>(sR, snap + 2 * (3 * n + 2), lane);
+    __syncthreads();
+    // park the inverses for compute_dz in tiles that phase 2 overwrites (moved into G there): Q_{b-1}^-1 in the left
+    // tile of row b, R_{b-1}^-1 in the right tile of row b-1, Q_{N-1}^-1 in the pad tile (left of row 0)
+    for (uint32_t i = t; i < nn; i += NT) Prow[i] = sQk_i[i];
+    for (uint32_t i = t; i < mm; i += NT) (Prow - 3 * nn)[2 * nn + i] = sR_i[i];
+    if (b == N - 1)
+        for (uint32_t i = t; i < nn; i += NT) Pinv[i] = sQp_i[i];
+    // ---- stage A: phi = A Q_k^-1, BR = B R_k^-1, gam = Q_kp1^-1 q_kp1  (:385-413)
+    for (uint32_t task = t; task < nn + nm + n; task += NT) {
+        if (task < nn) sPhi[task] = gemm_elem<false>(sA, sQk_i, n, n, n, task % n, task / n);
+        else if (task < nn + nm) { const uint32_t e = task - nn; sBR[e] = gemm_elem<false>(sB, sR_i, n, m, m, e % n, e / n); }
+        else { const uint32_t e = task - nn - nm; sgam[e] = matvec_elem(sQp_i, sqp, n, n, e); }
+    }
+    __syncthreads();
+    // ---- stage B: phi q_k, BR r_k, phi A^T, BR B^T  (:421-481)
+    for (uint32_t task = t; task < 2 * nn + 2 * n; task += NT) {
+        if (task < nn) sTh[task] = gemm_elem<true>(sPhi, sA, n, n, n, task % n, task / n);
+        else if (task < 2 * nn) { const uint32_t e = task - nn; sBRBt[e] = gemm_elem<true>(sBR, sB, n, m, n, e % n, e / n); }
+        else if (task < 2 * nn + n) { const uint32_t e = task - 2 * nn; sx0[e] = matvec_elem(sPhi, sqk, n, n, e); }
+        else { const uint32_t e = task - 2 * nn - n; sx1[e] = matvec_elem(sBR, srk, n, m, e); }
+    }
+    __syncthreads();
+    // ---- stage C: theta = (phi A^T + Q_kp1^-1) + BR B^T ; gamma ; S tiles  (:417, :441-443, :466-500, :527-560)
+    for (uint32_t i = t; i < nn; i += NT) {
+        const float th = __fadd_rn(__fadd_rn(sTh[i], sQp_i[i]), sBRBt[i]);
+        sTh[i] = th;
+        Srow[nn + i] = th * -1.0f;
+        Srow[i] = sPhi[i] * -1.0f;
+        (Srow - 3 * nn)[2 * nn + (i % n) * n + i / n] = sPhi[i] * -1.0f;      // phi^T: right tile of row b-1
+    }
+    for (uint32_t i = t; i < n; i += NT) {
+        const float gm = __fadd_rn(__fadd_rn(sgam[i], -sc[i]), __fadd_rn(sx1[i], sx0[i]));
+        gamma[(size_t)b * n + i] = gm * -1.0f;
+    }
+    identity(sTh_i, n, t, NT);
+    __syncthreads();
+    // ---- theta^-1 (:503-518)
+    if (warp == 0) gj_rcp_warp<n>(sTh, snap, lane);
+    __syncthreads();
+    for (uint32_t i = t; i < nn; i += NT) Prow[nn + i] = sTh_i[i] * -1.0f;
+}
+
+// ---- phase 2: off-diagonal tiles of Pinv (linsys_setup.cuh:9-137), plus moving the parked inverses into G
+template <uint32_t n, uint32_t m>
+__global__ void __launch_bounds__(SchurShape<n, m>::NT)
+schur_phase2_kernel(uint32_t N, float *__restrict__ G, const float *__restrict__ S, float *__restrict__ Pinv)
+{
+    using namespace schur_detail;
+    using K = SchurShape<n, m>;
+    constexpr uint32_t nn = K::nn, mm = K::mm, NT = K::NT;
+    extern __shared__ float sm[];
+    float *sTk = sm, *sTm = sTk + nn, *sTp = sTm + nn, *sPhik = sTp + nn, *sPhiT = sPhik + nn, *sL = sPhiT + nn, *sRr = sL + nn;
+    const uint32_t t = threadIdx.x, b = blockIdx.x;
+    float *Prow = Pinv + (size_t)b * 3 * nn;
+    const bool has_l = b != 0, has_r = b != N - 1;
+    // parked inverses -> G (this CTA owns the tiles they are parked in)
+    if (has_l)
+        for (uint32_t i = t; i < nn; i += NT) G[(size_t)(b - 1) * K::GSET + i] = Prow[i];
+    if (has_r)
+        for (uint32_t i = t; i < mm; i += NT) G[(size_t)b * K::GSET + nn + i] = Prow[2 * nn + i];
+    if (b == 0)
+        for (uint32_t i = t; i < nn; i += NT) G[(size_t)(N - 1) * K::GSET + i] = Prow[i];
+    for (uint32_t i = t; i < nn; i += NT) {
+        sTk[i] = Prow[nn + i];
+        if (has_l) { sTm[i] = (Prow - 3 * nn)[nn + i]; sPhik[i] = S[(size_t)b * 3 * nn + i]; }
+        if (has_r) { sTp[i] = (Prow + 3 * nn)[nn + i]; sPhiT[(i % n) * n + i / n] = S[(size_t)(b + 1) * 3 * nn + i]; }
+    }
+    __syncthreads();
+    for (uint32_t task = t; task < 2 * nn; task += NT) {
+        if (task < nn) { if (has_l) sL[task] = gemm_elem<false>(sTk, sPhik, n, n, n, task % n, task / n); }
+        else if (has_r) { const uint32_t e = task - nn; sRr[e] = gemm_elem<false>(sTk, sPhiT, n, n, n, e % n, e / n); }
+    }
+    __syncthreads();
+    for (uint32_t task = t; task < 2 * nn; task += NT) {
+        if (task < nn) { if (has_l) Prow[task] = gemm_elem<false>(sL, sTm, n, n, n, task % n, task / n) * -1.0f; }
+        else if (has_r) { const uint32_t e = task - nn; Prow[2 * nn + e] = gemm_elem<false>(sRr, sTp, n, n, n, e % n, e / n) * -1.0f; }
+    }
+}
+
+// ---- dz (dz.cuh:3-136): one CTA per knot does the state row and (k < N-1) the control row
+template <uint32_t n, uint32_t m>
+__global__ void __launch_bounds__(64)
+compute_dz_kernel(uint32_t N, const float *__restrict__ Ginv, const float *__restrict__ C, const float *__restrict__ g,
+                  const float *__restrict__ lambda, float *__restrict__ dz)
+{
+    using namespace schur_detail;
+    using K = SchurShape<n, m>;
+    constexpr uint32_t nn = K::nn, NT = 64;
+    __shared__ float sx[n], su[m > 0 ? m : 1], sl[n];
+    const uint32_t t = threadIdx.x, k = blockIdx.x;
+    const bool last = k == N - 1;
+    for (uint32_t i = t; i < n; i += NT) sl[i] = last ? 0.0f : lambda[(size_t)(k + 1) * n + i];
+    __syncthreads();
+    const float *A = C + (size_t)k * K::CSET, *B = A + nn;
+    for (uint32_t task = t; task < n + m; task += NT) {
+        if (task < n) {
+            float res = 0.0f;
+            if (!last)
+                for (uint32_t e = 0; e < n; ++e) res = fma_(A[task * n + e], sl[e], res);                  // (A^T lambda_{k+1})
+            const float s = __fadd_rn(lambda[(size_t)k * n + task], res);
+            sx[task] = __fadd_rn(g[(size_t)k * (n + m) + task], -s);
+        } else if (!last) {
+            const uint32_t i = task - n;
+            float res = 0.0f;
+            for (uint32_t e = 0; e < n; ++e) res = fma_(B[i * n + e], sl[e], res);                          // (B^T lambda_{k+1})
+            su[i] = __fadd_rn(g[(size_t)k * (n + m) + n + i], -res);
+        }
+    }
+    __syncthreads();
+    const float *Qi = Ginv + (size_t)k * K::GSET, *Ri = Qi + nn;
+    for (uint32_t task = t; task < n + m; task += NT) {
+        if (task < n) dz[(size_t)k * (n + m) + task] = matvec_elem(Qi, sx, n, n, task);
+        else if (!last) dz[(size_t)k * (n + m) + n + (task - n)] = matvec_elem(Ri, su, m, m, task - n);
+    }
+}
+
+}  // namespace gbd

@@ -121,6 +121,24 @@ int gbd_pcg_plan_solve_host_f64(gbd_pcg_plan *plan, const double *h_S, const dou
                                 const double *h_gamma, double *h_lambda, uint32_t max_iter, double exit_tol,
                                 uint32_t *h_iters, uint8_t *h_max_iter_exit);
 
+/*
+ * The two steps either side of the solve inside one SQP iteration, same layouts and
+ * bit-identical results:
+ *   gbd_form_schur_system_f32  replaces form_schur_system<float>(state_size, control_size, knot_points, d_G_dense,
+ *       d_C_dense, d_g, d_c, d_S, d_Pinv, d_gamma, rho)  (include/pcg/linsys_setup.cuh:621-657, called at
+ *       include/pcg/sqp.cuh:207): KKT blocks -> S, Pinv, gamma; d_G_dense is overwritten with the block inverses.
+ *       Two ordinary launches on `stream` (no cooperative launch, no co-residency requirement).
+ *   gbd_compute_dz_f32         replaces compute_dz<float>(state_size, control_size, knot_points, d_G_dense, d_C_dense,
+ *       d_g_val, d_lambda, d_dz)  (include/common/dz.cuh:125-136, called at include/pcg/sqp.cuh:250).
+ * Sizes: G (n*n+m*m)*(N-1)+n*n, C (n*n+n*m)*(N-1), g and dz (n+m)*(N-1)+n, c n*N.  (n, m) must be a compiled pair
+ * (gbd_schur_supported); GBD_PCG_ERR_UNSUPPORTED otherwise.
+ */
+int gbd_schur_supported(uint32_t n, uint32_t m);
+int gbd_form_schur_system_f32(uint32_t n, uint32_t m, uint32_t N, float *d_G, const float *d_C, const float *d_g,
+                              const float *d_c, float *d_S, float *d_Pinv, float *d_gamma, float rho, void *stream);
+int gbd_compute_dz_f32(uint32_t n, uint32_t m, uint32_t N, const float *d_Ginv, const float *d_C, const float *d_g,
+                       const float *d_lambda, float *d_dz, void *stream);
+
 /* Number of kernels this library has launched in this process (for bench.py's gpu_launches). */
 uint64_t gbd_pcg_launch_count(void);
 

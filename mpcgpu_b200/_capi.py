@@ -16,7 +16,8 @@ SYMBOLS = [
     "gbd_pcg_num_variants", "gbd_pcg_variant_at", "gbd_pcg_set_tuning", "gbd_pcg_solve_f32",
     "gbd_pcg_solve_f64", "gbd_pcg_linsys_f32", "gbd_pcg_solve_batched_f32", "gbd_pcg_plan_create",
     "gbd_pcg_plan_destroy", "gbd_pcg_plan_solve_host_f32", "gbd_pcg_plan_solve_host_f64",
-    "gbd_pcg_launch_count", "gbd_pcg_set_debug_buffer",
+    "gbd_pcg_launch_count", "gbd_pcg_set_debug_buffer", "gbd_schur_supported", "gbd_form_schur_system_f32",
+    "gbd_compute_dz_f32",
 ]
 
 _lib = None
@@ -70,6 +71,12 @@ def lib():
     L.gbd_pcg_plan_solve_host_f64.restype = C.c_int
     L.gbd_pcg_plan_solve_host_f64.argtypes = [vp, vp, vp, vp, vp, u32, f64, vp, vp]
     L.gbd_pcg_launch_count.restype = C.c_uint64
+    L.gbd_schur_supported.restype = C.c_int
+    L.gbd_schur_supported.argtypes = [u32, u32]
+    L.gbd_form_schur_system_f32.restype = C.c_int
+    L.gbd_form_schur_system_f32.argtypes = [u32, u32, u32, vp, vp, vp, vp, vp, vp, vp, f32, vp]
+    L.gbd_compute_dz_f32.restype = C.c_int
+    L.gbd_compute_dz_f32.argtypes = [u32, u32, u32, vp, vp, vp, vp, vp, vp]
     L.gbd_pcg_set_debug_buffer.restype = None
     L.gbd_pcg_set_debug_buffer.argtypes = [vp]
     _lib = L

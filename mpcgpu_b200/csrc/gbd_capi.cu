@@ -15,6 +15,7 @@
 #include "../../include/gbd/gbd_cluster_pcg_v3.cuh"
 #include "../../include/gbd/gbd_cluster_pcg_v4.cuh"
 #include "../../include/gbd/gbd_cluster_pcg_v5.cuh"
+#include "../../include/gbd/gbd_schur.cuh"
 #include <map>
 
 namespace {
@@ -531,6 +532,65 @@ int gbd_pcg_plan_solve_host_f64(gbd_pcg_plan *plan, const double *h_S, const dou
                                 uint8_t *h_max_iter_exit)
 {
     return plan_solve_host<double>(plan, h_S, h_Pinv, h_gamma, h_lambda, max_iter, exit_tol, h_iters, h_max_iter_exit);
+}
+
+}  // extern "C"
+
+namespace {
+template <uint32_t n, uint32_t m>
+int schur_launch(uint32_t N, float *G, const float *C, const float *g, const float *c, float *S, float *P, float *gam, float rho,
+                 cudaStream_t st)
+{
+    using K = gbd::SchurShape<n, m>;
+    gbd::schur_phase1_kernel<n, m><<<N, K::NT, K::P1_FLOATS * sizeof(float), st>>>(N, G, C, g, c, S, P, gam, rho);
+    gbd::schur_phase2_kernel<n, m><<<N, K::NT, K::P2_FLOATS * sizeof(float), st>>>(N, G, S, P);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e);
+    g_launches.fetch_add(2, std::memory_order_relaxed);
+    return GBD_PCG_OK;
+}
+template <uint32_t n, uint32_t m>
+int dz_launch(uint32_t N, const float *Gi, const float *C, const float *g, const float *lam, float *dz, cudaStream_t st)
+{
+    gbd::compute_dz_kernel<n, m><<<N, 64, 0, st>>>(N, Gi, C, g, lam, dz);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return GBD_PCG_OK;
+}
+}  // namespace
+
+// (state_size, control_size) pairs compiled in: IIWA (14, 7) and small shapes for tests
+#define GBD_SCHUR_SHAPES(X) X(14, 7) X(6, 3) X(4, 2) X(2, 1)
+
+extern "C" {
+
+int gbd_schur_supported(uint32_t n, uint32_t m)
+{
+#define X(a, b) if (n == a && m == b) return 1;
+    GBD_SCHUR_SHAPES(X)
+#undef X
+    return 0;
+}
+
+int gbd_form_schur_system_f32(uint32_t n, uint32_t m, uint32_t N, float *d_G, const float *d_C, const float *d_g,
+                              const float *d_c, float *d_S, float *d_Pinv, float *d_gamma, float rho, void *stream)
+{
+    if (!d_G || !d_C || !d_g || !d_c || !d_S || !d_Pinv || !d_gamma || N < 2) return GBD_PCG_ERR_BADARG;
+#define X(a, b) if (n == a && m == b) return schur_launch<a, b>(N, d_G, d_C, d_g, d_c, d_S, d_Pinv, d_gamma, rho, (cudaStream_t)stream);
+    GBD_SCHUR_SHAPES(X)
+#undef X
+    return GBD_PCG_ERR_UNSUPPORTED;
+}
+
+int gbd_compute_dz_f32(uint32_t n, uint32_t m, uint32_t N, const float *d_Ginv, const float *d_C, const float *d_g,
+                       const float *d_lambda, float *d_dz, void *stream)
+{
+    if (!d_Ginv || !d_C || !d_g || !d_lambda || !d_dz || N < 2) return GBD_PCG_ERR_BADARG;
+#define X(a, b) if (n == a && m == b) return dz_launch<a, b>(N, d_Ginv, d_C, d_g, d_lambda, d_dz, (cudaStream_t)stream);
+    GBD_SCHUR_SHAPES(X)
+#undef X
+    return GBD_PCG_ERR_UNSUPPORTED;
 }
 
 void gbd_pcg_set_debug_buffer(void *d_buf) { g_dbg = (uint32_t *)d_buf; }

@@ -167,3 +167,35 @@ def solvePCG(h_S, h_Pinv, h_gamma, h_lambda, stateSize, knotPoints, config: PcgC
         plan = _plans[key] = HostPlan(stateSize, knotPoints, 1, h_S.dtype)
     iters, flags = plan.solve(h_S, h_Pinv, h_gamma, h_lambda, config.pcg_max_iter, config.pcg_exit_tol)
     return (int(iters[0]), bool(flags[0])) if return_flag else int(iters[0])
+
+
+def form_schur_system(state_size, control_size, knot_points, d_G_dense, d_C_dense, d_g, d_c, d_S, d_Pinv, d_gamma, rho,
+                      stream=None):
+    """Mirror of form_schur_system<T> (include/pcg/linsys_setup.cuh:621-657, called at include/pcg/sqp.cuh:207): KKT blocks
+    -> S, Pinv, gamma in the pcg<> layout; d_G_dense is overwritten with the block inverses.  Asynchronous on `stream`."""
+    import torch
+    n, m, N = state_size, control_size, knot_points
+    want = dict(d_G_dense=(n * n + m * m) * (N - 1) + n * n, d_C_dense=(n * n + n * m) * (N - 1), d_g=(n + m) * (N - 1) + n,
+                d_c=n * N, d_S=3 * n * n * N, d_Pinv=3 * n * n * N, d_gamma=n * N)
+    for name, t in (("d_G_dense", d_G_dense), ("d_C_dense", d_C_dense), ("d_g", d_g), ("d_c", d_c), ("d_S", d_S),
+                    ("d_Pinv", d_Pinv), ("d_gamma", d_gamma)):
+        if not t.is_cuda or not t.is_contiguous() or t.dtype != torch.float32 or t.numel() != want[name]:
+            raise ValueError(f"{name}: expected a contiguous CUDA float32 tensor of {want[name]} elements")
+    _capi.check(_capi.lib().gbd_form_schur_system_f32(n, m, N, _ptr(d_G_dense), _ptr(d_C_dense), _ptr(d_g), _ptr(d_c), _ptr(d_S),
+                                                      _ptr(d_Pinv), _ptr(d_gamma), float(rho), _stream(stream)),
+                "gbd_form_schur_system_f32")
+
+
+def compute_dz(state_size, control_size, knot_points, d_G_dense, d_C_dense, d_g_val, d_lambda, d_dz, stream=None):
+    """Mirror of compute_dz<T> (include/common/dz.cuh:125-136, called at include/pcg/sqp.cuh:250); d_G_dense holds the block
+    inverses form_schur_system left there.  Asynchronous on `stream`."""
+    import torch
+    n, m, N = state_size, control_size, knot_points
+    want = dict(d_G_dense=(n * n + m * m) * (N - 1) + n * n, d_C_dense=(n * n + n * m) * (N - 1), d_g_val=(n + m) * (N - 1) + n,
+                d_lambda=n * N, d_dz=(n + m) * (N - 1) + n)
+    for name, t in (("d_G_dense", d_G_dense), ("d_C_dense", d_C_dense), ("d_g_val", d_g_val), ("d_lambda", d_lambda),
+                    ("d_dz", d_dz)):
+        if not t.is_cuda or not t.is_contiguous() or t.dtype != torch.float32 or t.numel() != want[name]:
+            raise ValueError(f"{name}: expected a contiguous CUDA float32 tensor of {want[name]} elements")
+    _capi.check(_capi.lib().gbd_compute_dz_f32(n, m, N, _ptr(d_G_dense), _ptr(d_C_dense), _ptr(d_g_val), _ptr(d_lambda),
+                                               _ptr(d_dz), _stream(stream)), "gbd_compute_dz_f32")

@@ -84,3 +84,37 @@ def linsys_window(n, N, S, Pinv, gamma, lam, ws: RefWorkspace, max_iter, tol, bl
     if us < 0:
         raise RuntimeError(f"reference linsys window failed rc={us}")
     return int(it.value), bool(fl.value), float(us)
+
+
+# ---- the reference's own Schur / preconditioner assembly and dz recovery (oracle/ref_schur_wrapper.cu)
+LIB_SCHUR = os.path.join(_HERE, "_ref", "libref_schur.so")
+_lschur = None
+
+
+def schur_available() -> bool:
+    return os.path.exists(LIB_SCHUR)
+
+
+def _libschur():
+    global _lschur
+    if _lschur is None:
+        _lschur = C.CDLL(LIB_SCHUR)
+        vp, u32 = C.c_void_p, C.c_uint32
+        _lschur.ref_form_schur_system_f32.restype = C.c_int
+        _lschur.ref_form_schur_system_f32.argtypes = [u32, u32, u32] + [vp] * 7 + [C.c_float]
+        _lschur.ref_compute_dz_f32.restype = C.c_int
+        _lschur.ref_compute_dz_f32.argtypes = [u32, u32, u32] + [vp] * 5
+    return _lschur
+
+
+def form_schur_system(n, m, N, G, Cm, g, c, S, Pinv, gamma, rho):
+    """Reference form_schur_system<float> on the default stream (cooperative launch); G is overwritten with the inverses."""
+    rc = _libschur().ref_form_schur_system_f32(n, m, N, *[int(t.data_ptr()) for t in (G, Cm, g, c, S, Pinv, gamma)], float(rho))
+    if rc:
+        raise RuntimeError(f"reference form_schur_system failed rc={rc}")
+
+
+def compute_dz(n, m, N, Ginv, Cm, g, lam, dz):
+    rc = _libschur().ref_compute_dz_f32(n, m, N, *[int(t.data_ptr()) for t in (Ginv, Cm, g, lam, dz)])
+    if rc:
+        raise RuntimeError(f"reference compute_dz failed rc={rc}")

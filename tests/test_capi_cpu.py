@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared_functions():
     txt = open(os.path.join(ROOT, "include", "gbd_pcg.h")).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    return sorted(set(re.findall(r"\b(gbd_pcg_[a-z0-9_]+)\s*\(", txt)))
+    return sorted(set(re.findall(r"\b(gbd_[a-z0-9_]+)\s*\(", txt)))
 
 
 def test_header_symbols_all_exported(capi):
@@ -22,7 +22,7 @@ def test_header_symbols_all_exported(capi):
     assert len(declared) >= 14
     assert sorted(capi.SYMBOLS) == declared
     out = subprocess.check_output(["nm", "-D", "--defined-only", capi.LIB_PATH], text=True)
-    exported = set(re.findall(r" T (gbd_pcg_\w+)", out))
+    exported = set(re.findall(r" T (gbd_\w+)", out))
     assert set(declared) <= exported
     L = capi.lib()
     for s in declared:

@@ -1,0 +1,111 @@
+"""GPU parity tests for rows f1 / f2 of SURVEY.md 8f: Schur-complement + preconditioner assembly (form_schur_system,
+include/pcg/linsys_setup.cuh:621-657) and step recovery (compute_dz, include/common/dz.cuh:125-136), through the C ABI.
+
+Tolerance: the kernels keep the reference's floating-point operation order, so the bar is BIT-EXACT (== on every
+element, +0/-0 equal) against the C oracle and -- when oracle/_ref/libref_schur.so is present -- against the
+reference's own kernels run on the same GPU.  Pad tiles (left of block row 0, right of block row N-1) are excluded:
+the reference never writes them."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("-m gpu tests need a CUDA device")
+    torch.cuda.init()
+    return torch
+
+
+def _mask_pads(x, n, N):
+    x = np.array(x, np.float32).reshape(N, 3, n, n).copy()
+    x[0, 0] = 0
+    x[N - 1, 2] = 0
+    return x
+
+
+def _ours(torch, n, m, N, G, C, g, c, rho):
+    import mpcgpu_b200 as mp
+    dG, dC, dg, dc = (torch.from_numpy(x.copy()).cuda() for x in (G, C, g, c))
+    dS = torch.full((3 * n * n * N,), float("nan"), device="cuda")
+    dP = torch.full((3 * n * n * N,), float("nan"), device="cuda")
+    dgam = torch.full((n * N,), float("nan"), device="cuda")
+    mp.form_schur_system(n, m, N, dG, dC, dg, dc, dS, dP, dgam, rho)
+    torch.cuda.synchronize()
+    return dict(S=dS, Pinv=dP, gamma=dgam, Ginv=dG, C=dC, g=dg)
+
+
+@pytest.mark.parametrize("n,m,N", [(14, 7, 8), (14, 7, 32), (14, 7, 128), (14, 7, 512), (6, 3, 12), (4, 2, 5), (2, 1, 3)])
+def test_form_schur_bit_exact_vs_oracle(torch_cuda, n, m, N):
+    from oracle import schur
+    G, C, g, c = schur.make_kkt(n, m, N, seed=100 + n + N)
+    want = schur.form(G, C, g, c, n, m, N, 1e-3)
+    got = _ours(torch_cuda, n, m, N, G, C, g, c, 1e-3)
+    assert np.array_equal(got["gamma"].cpu().numpy(), want["gamma"])
+    assert np.array_equal(got["Ginv"].cpu().numpy(), want["Ginv"])
+    for k in ("S", "Pinv"):
+        assert np.array_equal(_mask_pads(got[k].cpu().numpy(), n, N), _mask_pads(want[k], n, N)), k
+
+
+@pytest.mark.parametrize("n,m,N", [(14, 7, 32), (14, 7, 128), (6, 3, 12)])
+def test_form_schur_and_dz_bit_exact_vs_reference_kernels(torch_cuda, n, m, N):
+    """A/B against the reference's own form_schur_system / compute_dz compiled for sm_100a (oracle/_ref/libref_schur.so)."""
+    torch = torch_cuda
+    from oracle import refgpu, schur
+    if not refgpu.schur_available():
+        pytest.skip("oracle/_ref/libref_schur.so not built (make -C oracle ref needs /root/reference)")
+    import mpcgpu_b200 as mp
+    G, C, g, c = schur.make_kkt(n, m, N, seed=7)
+    got = _ours(torch, n, m, N, G, C, g, c, 1e-3)
+    rG, rC, rg, rc = (torch.from_numpy(x.copy()).cuda() for x in (G, C, g, c))
+    rS = torch.zeros(3 * n * n * N, device="cuda")
+    rP = torch.zeros(3 * n * n * N, device="cuda")
+    rgam = torch.zeros(n * N, device="cuda")
+    refgpu.form_schur_system(n, m, N, rG, rC, rg, rc, rS, rP, rgam, 1e-3)
+    torch.cuda.synchronize()
+    assert np.array_equal(got["gamma"].cpu().numpy(), rgam.cpu().numpy())
+    assert np.array_equal(got["Ginv"].cpu().numpy(), rG.cpu().numpy())
+    for k, r in (("S", rS), ("Pinv", rP)):
+        assert np.array_equal(_mask_pads(got[k].cpu().numpy(), n, N), _mask_pads(r.cpu().numpy(), n, N)), k
+    lam = torch.from_numpy(np.random.default_rng(1).standard_normal(n * N).astype(np.float32)).cuda()
+    dz_o = torch.zeros((n + m) * (N - 1) + n, device="cuda")
+    dz_r = torch.zeros_like(dz_o)
+    mp.compute_dz(n, m, N, got["Ginv"], got["C"], got["g"], lam, dz_o)
+    refgpu.compute_dz(n, m, N, rG, rC, rg, lam, dz_r)
+    torch.cuda.synchronize()
+    assert np.array_equal(dz_o.cpu().numpy(), dz_r.cpu().numpy())
+
+
+@pytest.mark.parametrize("n,m,N", [(14, 7, 32), (14, 7, 128)])
+def test_assemble_solve_recover_pipeline_vs_oracle(torch_cuda, n, m, N):
+    """form_schur_system -> pcg -> compute_dz on the GPU equals the same chain of oracles bit for bit."""
+    torch = torch_cuda
+    import mpcgpu_b200 as mp
+    from oracle import pcg as opcg
+    from oracle import schur
+    G, C, g, c = schur.make_kkt(n, m, N, seed=21)
+    got = _ours(torch, n, m, N, G, C, g, c, 1e-3)
+    lam = torch.zeros(n * N, device="cuda")
+    it = torch.zeros(1, dtype=torch.int32, device="cuda")
+    fl = torch.zeros(1, dtype=torch.uint8, device="cuda")
+    mp.pcg_launch(n, N, got["S"], got["Pinv"], got["gamma"], lam, None, None, None, None, it, fl, 200, 1e-6)
+    dz = torch.zeros((n + m) * (N - 1) + n, device="cuda")
+    mp.compute_dz(n, m, N, got["Ginv"], got["C"], got["g"], lam, dz)
+    torch.cuda.synchronize()
+    o = schur.form(G, C, g, c, n, m, N, 1e-3)
+    w = opcg.pcg(o["S"], o["Pinv"], o["gamma"], np.zeros(n * N, np.float32), n, N, 200, 1e-6)
+    assert int(it.item()) == w["iters"] and bool(fl.item()) == w["max_iter_exit"]
+    assert np.array_equal(lam.cpu().numpy(), w["lam"])
+    assert np.array_equal(dz.cpu().numpy(), schur.dz(o["Ginv"], C, g, w["lam"], n, m, N))
+
+
+def test_schur_argument_errors(torch_cuda):
+    from mpcgpu_b200 import _capi
+    L = _capi.lib()
+    assert L.gbd_schur_supported(14, 7) == 1 and L.gbd_schur_supported(14, 6) == 0
+    assert L.gbd_form_schur_system_f32(14, 6, 8, 1, 1, 1, 1, 1, 1, 1, 1e-3, 0) == _capi.ERR_UNSUPPORTED
+    assert L.gbd_form_schur_system_f32(14, 7, 8, 0, 1, 1, 1, 1, 1, 1, 1e-3, 0) == _capi.ERR_BADARG
+    assert L.gbd_compute_dz_f32(14, 7, 1, 1, 1, 1, 1, 1, 0) == _capi.ERR_BADARG
