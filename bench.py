@@ -486,6 +486,58 @@ def run_ours(args):
             except Exception as e:                             # the extras never fail the bench line
                 others.append({"config": what, "error": repr(e)[:200]})
         extras["other_configs"] = others
+    # ---------------- rows f1 / f2: Schur + preconditioner assembly and dz recovery around the solve
+    if rank == 0 and not args.no_configs:
+        try:
+            mctl = n // 2
+            rngk = np.random.default_rng(99)
+            Gs, Cs, gs = [], [], []
+            for kk in range(N):
+                Mq = rngk.standard_normal((n, n))
+                Gs.append((Mq @ Mq.T / n + np.eye(n)).T.ravel())
+                gs.append(rngk.standard_normal(n))
+                if kk < N - 1:
+                    Mr = rngk.standard_normal((mctl, mctl))
+                    Gs.append((Mr @ Mr.T / mctl + np.eye(mctl)).T.ravel())
+                    Cs.append((np.eye(n) + rngk.standard_normal((n, n)) / 16).T.ravel())
+                    Cs.append((rngk.standard_normal((n, mctl)) / 16).T.ravel())
+                    gs.append(rngk.standard_normal(mctl))
+            kG0, kC, kg = (torch.from_numpy(np.concatenate(x).astype(np.float32)).to(dev) for x in (Gs, Cs, gs))
+            kc = torch.from_numpy((0.1 * rngk.standard_normal(n * N)).astype(np.float32)).to(dev)
+            kG = kG0.clone()
+            kS, kP = torch.zeros(3 * n * n * N, device=dev), torch.zeros(3 * n * n * N, device=dev)
+            kgam, klam = torch.zeros(n * N, device=dev), torch.randn(n * N, device=dev)
+            kdz = torch.zeros((n + mctl) * (N - 1) + n, device=dev)
+
+            def t_us(fn, reps=200):
+                for _ in range(10):
+                    fn()
+                torch.cuda.synchronize()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                for _ in range(reps):
+                    fn()
+                a1.record()
+                torch.cuda.synchronize()
+                return 1e3 * a0.elapsed_time(a1) / reps
+
+            pk = [int(x.data_ptr()) for x in (kG, kC, kg, kc, kS, kP, kgam, klam, kdz)]
+
+            def f_schur():
+                kG.copy_(kG0)
+                rc = L.gbd_form_schur_system_f32(n, mctl, N, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], 1e-3, stream)
+                assert rc == 0, rc
+
+            t_cp = t_us(lambda: kG.copy_(kG0))
+            t_fs = t_us(f_schur) - t_cp
+            t_dzz = t_us(lambda: L.gbd_compute_dz_f32(n, mctl, N, pk[0], pk[1], pk[2], pk[7], pk[8], stream))
+            extras["sqp_neighbours"] = {
+                "what": "rows f1/f2: gbd_form_schur_system_f32 (replaces form_schur_system, include/pcg/linsys_setup.cuh:621-657) and "
+                        "gbd_compute_dz_f32 (replaces compute_dz, include/common/dz.cuh:125-136), n=14 m=7 N=128, device-resident, "
+                        "back-to-back launches; reference kernels on the same box: profiles/r01c_ab_schur.json",
+                "form_schur_us": t_fs, "compute_dz_us": t_dzz, "launches_per_call": {"form_schur": 2, "compute_dz": 1}}
+        except Exception as e:                                 # the extras never fail the bench line
+            extras["sqp_neighbours"] = {"error": repr(e)[:200]}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline({k: (host[k][:64] if isinstance(host[k], np.ndarray) else host[k]) for k in host},

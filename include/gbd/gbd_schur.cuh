@@ -33,52 +33,56 @@ namespace schur_detail {
 
 __device__ __forceinline__ float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 
-// Gauss-Jordan on [V | I] (DIM x 2 DIM, column-major) by ONE warp, the reference's several-matrices-at-once
-// arithmetic (matrix.cuh:149-238): per pivot p and for the DIM+1 columns p .. p+DIM,
-//   row == p : x /= piv         else : x = fma(-(col[row] / piv), rowv[col], x)
-template <uint32_t DIM>
-__device__ __forceinline__ void gj_div_warp(float *A, float *snap, uint32_t lane)
+// Gauss-Jordan on [V | I] (DIM x 2 DIM, column-major) by ONE warp.  Per pivot p the reference updates the DIM+1
+// columns p .. p+DIM from a snapshot of the pivot column `col` and pivot row `rowv`:
+//   several-matrices form (matrix.cuh:149-238, DIV = true):  row == p : x / piv      else : fma(-(col[row] / piv), rowv[c], x)
+//   single-matrix form    (matrix.cuh:120-146, DIV = false): pvInv = 1 / piv;
+//                                                            row == p : x * pvInv    else : fma(-(col[row] * pvInv), rowv[c], x)
+// Here every division of a pivot step is issued at once in step (a): lanes 0..DIM-1 form the row factors col[row]/piv
+// (resp. col[row]*pvInv), lanes 16.. the new pivot row; step (b) is then one FMA per element with all of a lane's
+// elements in flight together.  Same operands and operations per element as the reference -> same bits.
+template <uint32_t DIM, bool DIV>
+__device__ __forceinline__ void gj_warp(float *A, float *snap, uint32_t lane)
 {
-    float *colv = snap, *rowv = snap + DIM, *f = snap + 2 * DIM + 1;
+    static_assert(DIM + 1 <= 16, "one warp: factors in lanes 0..15, pivot row in lanes 16..31");
+    float *rowv = snap, *f = snap + (DIM + 1), *nrow = f + DIM;      // DIM+1, DIM, DIM+1 floats
+    constexpr uint32_t ELEMS = DIM * (DIM + 1), PER = (ELEMS + 31) / 32;
     for (uint32_t p = 0; p < DIM; ++p) {
         const uint32_t off = p * DIM;
-        for (uint32_t i = lane; i < DIM; i += 32) colv[i] = A[i + off];
-        for (uint32_t i = lane; i < DIM + 1; i += 32) rowv[i] = A[i * DIM + p + off];
+        const float piv = A[p + off];
+        // ---- (a) snapshot + all divisions of this pivot step
+        if (lane < DIM) {
+            const float cv = A[lane + off];
+            f[lane] = DIV ? __fdiv_rn(cv, piv) : __fmul_rn(cv, __fdiv_rn(1.0f, piv));
+        } else if (lane >= 16 && lane < 16 + DIM + 1) {
+            const uint32_t cI = lane - 16;
+            const float rv = A[cI * DIM + p + off];
+            rowv[cI] = rv;
+            nrow[cI] = DIV ? __fdiv_rn(rv, piv) : __fmul_rn(rv, __fdiv_rn(1.0f, piv));
+        }
         __syncwarp();
-        const float piv = colv[p];
-        for (uint32_t i = lane; i < DIM; i += 32) f[i] = __fdiv_rn(colv[i], piv);
-        __syncwarp();
-        for (uint32_t ind = lane; ind < DIM * (DIM + 1); ind += 32) {
-            const uint32_t row = ind % DIM, col = ind / DIM;
-            const float x = A[off + ind];
-            A[off + ind] = (row == p) ? __fdiv_rn(x, piv) : fma_(-f[row], rowv[col], x);
+        // ---- (b) one FMA per element, all of this lane's elements in flight together
+        float x[PER];
+#pragma unroll
+        for (uint32_t q = 0; q < PER; ++q) {
+            const uint32_t ind = lane + 32 * q;
+            x[q] = ind < ELEMS ? A[off + ind] : 0.0f;
+        }
+#pragma unroll
+        for (uint32_t q = 0; q < PER; ++q) {
+            const uint32_t ind = lane + 32 * q;
+            if (ind < ELEMS) {
+                const uint32_t row = ind % DIM, col = ind / DIM;
+                A[off + ind] = (row == p) ? nrow[col] : fma_(-f[row], rowv[col], x[q]);
+            }
         }
         __syncwarp();
     }
 }
-
-// the reference's single-matrix arithmetic (matrix.cuh:120-146): pvInv = 1 / piv,
-//   row == p : x *= pvInv       else : x = fma(-(col[row] * pvInv), rowv[col], x)
 template <uint32_t DIM>
-__device__ __forceinline__ void gj_rcp_warp(float *A, float *snap, uint32_t lane)
-{
-    float *colv = snap, *rowv = snap + DIM, *f = snap + 2 * DIM + 1;
-    for (uint32_t p = 0; p < DIM; ++p) {
-        const uint32_t off = p * DIM;
-        for (uint32_t i = lane; i < DIM; i += 32) colv[i] = A[i + off];
-        for (uint32_t i = lane; i < DIM + 1; i += 32) rowv[i] = A[i * DIM + p + off];
-        __syncwarp();
-        const float pv_inv = __fdiv_rn(1.0f, colv[p]);
-        for (uint32_t i = lane; i < DIM; i += 32) f[i] = __fmul_rn(colv[i], pv_inv);
-        __syncwarp();
-        for (uint32_t ind = lane; ind < DIM * (DIM + 1); ind += 32) {
-            const uint32_t row = ind % DIM, col = ind / DIM;
-            const float x = A[off + ind];
-            A[off + ind] = (row == p) ? __fmul_rn(x, pv_inv) : fma_(-f[row], rowv[col], x);
-        }
-        __syncwarp();
-    }
-}
+__device__ __forceinline__ void gj_div_warp(float *A, float *snap, uint32_t lane) { gj_warp<DIM, true>(A, snap, lane); }
+template <uint32_t DIM>
+__device__ __forceinline__ void gj_rcp_warp(float *A, float *snap, uint32_t lane) { gj_warp<DIM, false>(A, snap, lane); }
 
 // one element of C (M x NC) = A (M x K) * B (K x NC)  [TB: A * B^T with B stored NC x K], column-major,
 // one FMA per term in ascending k (GLASS/src/L3/gemm.cuh:47-96)
@@ -111,7 +115,7 @@ struct SchurShape {
     static constexpr uint32_t GSET = nn + mm, CSET = nn + nm;
     // phase-1 shared memory (floats)
     static constexpr uint32_t P1_FLOATS = nn /*A*/ + nm /*B*/ + 2 * nn /*Qk|I*/ + 2 * nn /*Qkp1|I*/ + 2 * mm /*R|I*/ + nn /*phi*/ + nm /*BR*/ +
-                                          2 * nn /*theta|I*/ + nn /*BRBt*/ + 6 * n + m + 3 * (3 * n + 2);
+                                          2 * nn /*theta|I*/ + nn /*BRBt*/ + 6 * n + m + 3 * (3 * n + 2);   // 3 snapshots: pivot row, row factors, new pivot row
     static constexpr uint32_t P2_FLOATS = 7 * nn;
 };
 
@@ -125,6 +129,7 @@ schur_phase1_kernel(uint32_t N, const float *__restrict__ G, const float *__rest
     using K = SchurShape<n, m>;
     constexpr uint32_t nn = K::nn, mm = K::mm, nm = K::nm, NT = K::NT;
     extern __shared__ float sm[];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // phase 2 may be scheduled; it waits for our completion
     float *sA = sm, *sB = sA + nn, *sQk = sB + nm, *sQk_i = sQk + nn, *sQp = sQk_i + nn, *sQp_i = sQp + nn;
     float *sR = sQp_i + nn, *sR_i = sR + mm, *sPhi = sR_i + mm, *sBR = sPhi + nn, *sTh = sBR + nm, *sTh_i = sTh + nn;
     float *sBRBt = sTh_i + nn, *sqk = sBRBt + nn, *sqp = sqk + n, *srk = sqp + n, *sgam = srk + m, *sx0 = sgam + n, *sx1 = sx0 + n;
@@ -212,6 +217,7 @@ schur_phase1_kernel(uint32_t N, const float *__restrict__ G, const float *__rest
     for (uint32_t i = t; i < nn; i += NT) Prow[nn + i] = sTh_i[i] * -1.0f;
 }
 
+
 // ---- phase 2: off-diagonal tiles of Pinv (linsys_setup.cuh:9-137), plus moving the parked inverses into G
 template <uint32_t n, uint32_t m>
 __global__ void __launch_bounds__(SchurShape<n, m>::NT)
@@ -225,6 +231,9 @@ schur_phase2_kernel(uint32_t N, float *__restrict__ G, const float *__restrict__
     const uint32_t t = threadIdx.x, b = blockIdx.x;
     float *Prow = Pinv + (size_t)b * 3 * nn;
     const bool has_l = b != 0, has_r = b != N - 1;
+    // launched with programmatic stream serialization: this grid may be scheduled while phase 1 drains; everything
+    // phase 1 wrote is visible after this wait
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     // parked inverses -> G (this CTA owns the tiles they are parked in)
     if (has_l)
         for (uint32_t i = t; i < nn; i += NT) G[(size_t)(b - 1) * K::GSET + i] = Prow[i];

@@ -543,7 +543,19 @@ int schur_launch(uint32_t N, float *G, const float *C, const float *g, const flo
 {
     using K = gbd::SchurShape<n, m>;
     gbd::schur_phase1_kernel<n, m><<<N, K::NT, K::P1_FLOATS * sizeof(float), st>>>(N, G, C, g, c, S, P, gam, rho);
-    gbd::schur_phase2_kernel<n, m><<<N, K::NT, K::P2_FLOATS * sizeof(float), st>>>(N, G, S, P);
+    {   // phase 2 with programmatic stream serialization: its launch overlaps phase 1, griddepcontrol.wait orders the data
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute at[1];
+        cfg.gridDim = dim3(N);
+        cfg.blockDim = dim3(K::NT);
+        cfg.dynamicSmemBytes = K::P2_FLOATS * sizeof(float);
+        cfg.stream = st;
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        const float *Sc = S;
+        CK(cudaLaunchKernelEx(&cfg, gbd::schur_phase2_kernel<n, m>, N, G, Sc, P));
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e);
     g_launches.fetch_add(2, std::memory_order_relaxed);

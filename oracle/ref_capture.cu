@@ -10,7 +10,10 @@
 //   ref_capture <traj.csv> <eepos.traj> <out.bin> <knot offset> <count> <perturb 0|1> [mode bits]
 // mode bits (debug aid): 1 = do not pre-fill S/Pinv with 0xFF; 2 = run compute_merit first as sqp.cuh:173 does;
 // 4 = create the cuBLAS handle and 8 streams first as sqp.cuh:64-72 does; 8 = run the PCG kernel after the assembly
-// exactly as sqp.cuh:230 launches it and append lambda (n*N floats), iters, flag to the record.
+// exactly as sqp.cuh:230 launches it and append lambda (n*N floats), iters, flag to the record;
+// 16 = also write <out.bin>.kkt: G, C, g, c as generate_kkt_submatrices left them (the inputs of form_schur_system),
+// then G after form_schur_system (the block inverses), and -- with bit 8 -- dz from the reference's compute_dz on the
+// PCG solution (golden vectors for rows f1 / f2, tools/make_golden_schur.py).
 // count > 1 with perturb = 1 builds BASELINE config 4's batch: system i = the window at <offset> plus
 // N(0, 0.05^2) on q, N(0, 0.01^2) on qd, N(0, 1) on u, std::mt19937_64(1234 + i).
 #include <cstdio>
@@ -82,6 +85,14 @@ int main(int argc, char **argv)
     gpuErrchk(cudaMalloc(&d_fl, sizeof(bool)));
 
     FILE *f = fopen(argv[3], "wb");
+    FILE *fk = (mode & 16) ? fopen((std::string(argv[3]) + ".kkt").c_str(), "wb") : nullptr;
+    auto dump_dev = [&](FILE *fp, const linsys_t *d, size_t bytes) {
+        std::vector<char> h(bytes);
+        gpuErrchk(cudaMemcpy(h.data(), d, bytes, cudaMemcpyDeviceToHost));
+        fwrite(h.data(), 1, bytes, fp);
+    };
+    linsys_t *d_dz = nullptr;
+    if (fk) gpuErrchk(cudaMalloc(&d_dz, g_bytes));
     std::vector<linsys_t> hS(mat), hP(mat), hg(vec);
     for (uint32_t i = 0; i < count; i++) {
         std::vector<linsys_t> xu = xu0;
@@ -110,6 +121,10 @@ int main(int argc, char **argv)
         generate_kkt_submatrices<linsys_t><<<knot_points, KKT_THREADS, 2 * get_kkt_smem_size<linsys_t>(state_size, control_size)>>>(
             state_size, control_size, knot_points, d_G, d_C, d_g, d_c, d_dynmem, timestep, d_ee, d_xs, d_xu);
         gpuErrchk(cudaPeekAtLastError());
+        if (fk) {
+            gpuErrchk(cudaDeviceSynchronize());
+            dump_dev(fk, d_G, G_bytes); dump_dev(fk, d_C, C_bytes); dump_dev(fk, d_g, g_bytes); dump_dev(fk, d_c, c_bytes);
+        }
         form_schur_system<linsys_t>(state_size, control_size, knot_points, d_G, d_C, d_g, d_c, d_S, d_Pinv, d_gamma, rho);
         gpuErrchk(cudaPeekAtLastError());
         gpuErrchk(cudaDeviceSynchronize());
@@ -119,6 +134,7 @@ int main(int argc, char **argv)
         fwrite(hS.data(), sizeof(linsys_t), mat, f);
         fwrite(hP.data(), sizeof(linsys_t), mat, f);
         fwrite(hg.data(), sizeof(linsys_t), vec, f);
+        if (fk) dump_dev(fk, d_G, G_bytes);
         if (mode & 8) {
             pcg_config<linsys_t> config;
             config.pcg_exit_tol = 1e-4;
@@ -137,9 +153,15 @@ int main(int argc, char **argv)
             uint32_t tail[2] = {it, (uint32_t)fl};
             fwrite(tail, sizeof(uint32_t), 2, f);
             printf("  pcg: iters %u max_iter_exit %d\n", it, (int)fl);
+            if (fk) {
+                compute_dz<linsys_t>(state_size, control_size, knot_points, d_G, d_C, d_g, d_lambda, d_dz);
+                gpuErrchk(cudaDeviceSynchronize());
+                dump_dev(fk, d_dz, g_bytes);
+            }
         }
     }
     fclose(f);
+    if (fk) fclose(fk);
     printf("captured %u system(s): n=%u N=%u offset=%u perturb=%d -> %s\n", count, state_size, knot_points, offset, (int)perturb, argv[3]);
     return 0;
 }

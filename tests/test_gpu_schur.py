@@ -109,3 +109,33 @@ def test_schur_argument_errors(torch_cuda):
     assert L.gbd_form_schur_system_f32(14, 6, 8, 1, 1, 1, 1, 1, 1, 1, 1e-3, 0) == _capi.ERR_UNSUPPORTED
     assert L.gbd_form_schur_system_f32(14, 7, 8, 0, 1, 1, 1, 1, 1, 1, 1e-3, 0) == _capi.ERR_BADARG
     assert L.gbd_compute_dz_f32(14, 7, 1, 1, 1, 1, 1, 1, 0) == _capi.ERR_BADARG
+
+
+def test_form_schur_and_dz_on_reference_minted_iiwa_vectors(torch_cuda):
+    """tests/golden/schur_iiwa_*.npz: inputs from the reference's generate_kkt_submatrices on examples/trajfiles/0_0_*, answers
+    from the reference's form_schur_system / pcg<> / compute_dz (tools/make_golden_schur.py) -- bit-exact."""
+    import glob
+    import os
+    import mpcgpu_b200 as mp
+    torch = torch_cuda
+    paths = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "schur_iiwa_*.npz")))
+    assert paths
+    for path in paths:
+        z = np.load(path)
+        n, m, N, rho = int(z["n"]), int(z["m"]), int(z["N"]), float(z["rho"])
+        got = _ours(torch, n, m, N, z["G"], z["C"], z["g"], z["c"], rho)
+        assert np.array_equal(got["gamma"].cpu().numpy(), z["gamma"])
+        assert np.array_equal(got["Ginv"].cpu().numpy(), z["Ginv"])
+        for k in ("S", "Pinv"):
+            assert np.array_equal(_mask_pads(got[k].cpu().numpy(), n, N), _mask_pads(z[k], n, N)), k
+        # solve with the reference's tolerance / cap, then recover dz: the whole chain equals the reference's
+        lam = torch.zeros(n * N, device="cuda")
+        it = torch.zeros(1, dtype=torch.int32, device="cuda")
+        fl = torch.zeros(1, dtype=torch.uint8, device="cuda")
+        mp.pcg_launch(n, N, got["S"], got["Pinv"], got["gamma"], lam, None, None, None, None, it, fl, 173, 1e-4)
+        dz = torch.zeros((n + m) * (N - 1) + n, device="cuda")
+        mp.compute_dz(n, m, N, got["Ginv"], got["C"], got["g"], lam, dz)
+        torch.cuda.synchronize()
+        assert int(it.item()) == int(z["pcg_iters"])
+        assert np.array_equal(lam.cpu().numpy(), z["lam"])
+        assert np.array_equal(dz.cpu().numpy(), z["dz"])

@@ -68,3 +68,34 @@ def test_dz_matches_fp64():
             du = Ri @ (g[k * (n + m) + n:(k + 1) * (n + m)].astype(np.float64) - B.T @ lam[(k + 1) * n:(k + 2) * n])
             np.testing.assert_allclose(dz[k * (n + m) + n:(k + 1) * (n + m)], du, rtol=2e-4, atol=2e-5)
         np.testing.assert_allclose(dz[k * (n + m):k * (n + m) + n], Qi @ rhs, rtol=2e-4, atol=2e-5)
+
+
+# ---- pinned against the REFERENCE: tests/golden/schur_iiwa_*.npz were minted on a B200 by tools/make_golden_schur.py from the
+# reference's own generate_kkt_submatrices -> form_schur_system -> pcg<> -> compute_dz on examples/trajfiles/0_0_*.
+import glob
+import os
+
+GOLDEN_SCHUR = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "schur_iiwa_*.npz")))
+
+
+def _mask_pads(x, n, N):
+    x = np.array(x, np.float32).reshape(N, 3, n, n).copy()
+    x[0, 0] = 0
+    x[N - 1, 2] = 0
+    return x
+
+
+@pytest.mark.parametrize("path", GOLDEN_SCHUR, ids=[os.path.basename(p) for p in GOLDEN_SCHUR])
+def test_oracle_bit_exact_on_reference_minted_vectors(path):
+    z = np.load(path)
+    n, m, N, rho = int(z["n"]), int(z["m"]), int(z["N"]), float(z["rho"])
+    o = schur.form(z["G"], z["C"], z["g"], z["c"], n, m, N, rho)
+    assert np.array_equal(o["gamma"], z["gamma"])
+    assert np.array_equal(o["Ginv"], z["Ginv"])
+    for k in ("S", "Pinv"):
+        assert np.array_equal(_mask_pads(o[k], n, N), _mask_pads(z[k], n, N)), k
+    assert np.array_equal(schur.dz(z["Ginv"], z["C"], z["g"], z["lam"], n, m, N), z["dz"])
+
+
+def test_golden_schur_fixtures_present():
+    assert len(GOLDEN_SCHUR) >= 2
