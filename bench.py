@@ -401,6 +401,38 @@ def run_ours(args):
                                 "unit": "GB/s", "frac": bi / Kb * b_iter / bsec / 1e9 / world / peak,
                                 "compulsory_gbs": Bl * esz * (2 * (3 * N - 2) * n * n + 4 * N * n) / bsec / 1e9}}
         launches_b = Kb
+        # ---- the same batch as whole SQP linear-system steps (row f3): KKT blocks in, dz out; assembly -> solve -> dz per
+        # shard in one enqueue (4 launches), then the flag all-gather
+        try:
+            from mpcgpu_b200.sharding import ShardedStep
+            mctl = n // 2
+            kG, kC, kg, kc = (torch.from_numpy(x).to(dev) for x in synth.make_kkt_batch(n, mctl, N, Bl, seed=7000 + rank))
+            Ks = 3
+            kGs = [kG.clone().reshape(-1) for _ in range(Ks + 1)]
+            kC, kg, kc = kC.reshape(-1), kg.reshape(-1), kc.reshape(-1)
+            slam = torch.zeros(Ks + 1, Bl * n * N, device=dev)
+            sdz = torch.zeros(Bl * ((n + mctl) * (N - 1) + n), device=dev)
+            sstep = ShardedStep(n, mctl, N, BATCH_TOTAL, world, rank)
+            sstep.step(kGs[Ks], kC, kg, kc, 1e-3, slam[Ks], sdz, MAX_ITER, EXIT_TOL)
+            barrier()
+            s_ms = 0.0
+            for q in range(Ks):
+                if flush is not None:
+                    flush.fill_(q & 0xFF)
+                s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                barrier()
+                s0.record()
+                gflags = sstep.step(kGs[q], kC, kg, kc, 1e-3, slam[q], sdz, MAX_ITER, EXIT_TOL)
+                s1.record()
+                torch.cuda.synchronize()
+                s_ms += max_over_ranks(s0.elapsed_time(s1))
+            sit, _ = sstep.plan.results()
+            batched["sqp_step"] = {"what": "gbd_step_run_f32 per shard (form_schur_system -> pcg -> compute_dz, 4 launches, no host "
+                                           "round trip) + flag all-gather; synthetic KKT blocks (mpcgpu_b200/synth.py make_kkt_batch)",
+                                   "traj_per_sec": world * Bl / (s_ms * 1e-3 / Ks), "ms_per_step": s_ms / Ks, "steps": Ks,
+                                   "mean_iters_rank0": float(sit.mean()), "converged_frac_all": float((gflags == 0).float().mean().item())}
+        except Exception as e:                                 # never fails the bench line
+            batched["sqp_step"] = {"error": repr(e)[:200]}
     # ---------------- extras (rank 0): the reference-minted IIWA system and the header drop-in pcg<> under the
     # reference's own launch geometry (cooperative, grid = N, 128 threads), both on tests/golden/iiwa_128_0.npz
     extras = {}

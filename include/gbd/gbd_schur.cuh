@@ -135,6 +135,11 @@ schur_phase1_kernel(uint32_t N, const float *__restrict__ G, const float *__rest
     float *sBRBt = sTh_i + nn, *sqk = sBRBt + nn, *sqp = sqk + n, *srk = sqp + n, *sgam = srk + m, *sx0 = sgam + n, *sx1 = sx0 + n;
     float *sc = sx1 + n, *snap = sc + n;                      // 3 snapshots of 3n+2 floats
     const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5, b = blockIdx.x;
+    {   // blockIdx.y = system of a batch: every array carries a leading [batch] dimension
+        const size_t sys = blockIdx.y;
+        G += sys * ((size_t)K::GSET * (N - 1) + nn); C += sys * (size_t)K::CSET * (N - 1); g += sys * ((size_t)(n + m) * (N - 1) + n);
+        c += sys * (size_t)n * N; S += sys * 3 * (size_t)nn * N; Pinv += sys * 3 * (size_t)nn * N; gamma += sys * (size_t)n * N;
+    }
     float *Srow = S + (size_t)b * 3 * nn, *Prow = Pinv + (size_t)b * 3 * nn;
 
     if (b == 0) {
@@ -229,6 +234,10 @@ schur_phase2_kernel(uint32_t N, float *__restrict__ G, const float *__restrict__
     extern __shared__ float sm[];
     float *sTk = sm, *sTm = sTk + nn, *sTp = sTm + nn, *sPhik = sTp + nn, *sPhiT = sPhik + nn, *sL = sPhiT + nn, *sRr = sL + nn;
     const uint32_t t = threadIdx.x, b = blockIdx.x;
+    {
+        const size_t sys = blockIdx.y;
+        G += sys * ((size_t)K::GSET * (N - 1) + nn); S += sys * 3 * (size_t)nn * N; Pinv += sys * 3 * (size_t)nn * N;
+    }
     float *Prow = Pinv + (size_t)b * 3 * nn;
     const bool has_l = b != 0, has_r = b != N - 1;
     // launched with programmatic stream serialization: this grid may be scheduled while phase 1 drains; everything
@@ -269,6 +278,11 @@ compute_dz_kernel(uint32_t N, const float *__restrict__ Ginv, const float *__res
     constexpr uint32_t nn = K::nn, NT = 64;
     __shared__ float sx[n], su[m > 0 ? m : 1], sl[n];
     const uint32_t t = threadIdx.x, k = blockIdx.x;
+    {
+        const size_t sys = blockIdx.y;
+        Ginv += sys * ((size_t)K::GSET * (N - 1) + nn); C += sys * (size_t)K::CSET * (N - 1); g += sys * ((size_t)(n + m) * (N - 1) + n);
+        lambda += sys * (size_t)n * N; dz += sys * ((size_t)(n + m) * (N - 1) + n);
+    }
     const bool last = k == N - 1;
     for (uint32_t i = t; i < n; i += NT) sl[i] = last ? 0.0f : lambda[(size_t)(k + 1) * n + i];
     __syncthreads();

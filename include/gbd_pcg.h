@@ -139,6 +139,23 @@ int gbd_form_schur_system_f32(uint32_t n, uint32_t m, uint32_t N, float *d_G, co
 int gbd_compute_dz_f32(uint32_t n, uint32_t m, uint32_t N, const float *d_Ginv, const float *d_C, const float *d_g,
                        const float *d_lambda, float *d_dz, void *stream);
 
+/*
+ * One SQP linear-system step for `batch` trajectories: what include/pcg/sqp.cuh:207-258 does per SQP
+ * iteration -- form_schur_system, the pcg<> launch with two blocking read-backs, compute_dz -- enqueued on `stream` as
+ * assembly -> solve (warm-started from d_lambda, in/out) -> dz with no host round trip in between.  The plan owns S, Pinv,
+ * gamma and the result slots (the reference cudaMallocs them on every sqpSolvePcg call, sqp.cuh:94-135).  All arrays carry a
+ * leading [batch] dimension; d_G is overwritten with the block inverses as form_schur_system does.
+ * gbd_step_results blocks on `stream` and returns the per-trajectory iteration counts and max_iter_exit flags of the last
+ * run; gbd_step_device_flags is the device copy of the flags (what the multi-GPU driver all-gathers per outer step).
+ */
+typedef struct gbd_step_plan gbd_step_plan;
+int gbd_step_plan_create(uint32_t n, uint32_t m, uint32_t N, uint32_t batch, gbd_step_plan **out);
+int gbd_step_plan_destroy(gbd_step_plan *plan);
+int gbd_step_run_f32(gbd_step_plan *plan, float *d_G, const float *d_C, const float *d_g, const float *d_c, float rho,
+                     float *d_lambda, float *d_dz, uint32_t max_iter, float exit_tol, void *stream);
+int gbd_step_results(gbd_step_plan *plan, uint32_t *h_iters, uint8_t *h_max_iter_exit, void *stream);
+const uint8_t *gbd_step_device_flags(gbd_step_plan *plan);
+
 /* Number of kernels this library has launched in this process (for bench.py's gpu_launches). */
 uint64_t gbd_pcg_launch_count(void);
 

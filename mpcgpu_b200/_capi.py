@@ -17,7 +17,8 @@ SYMBOLS = [
     "gbd_pcg_solve_f64", "gbd_pcg_linsys_f32", "gbd_pcg_solve_batched_f32", "gbd_pcg_plan_create",
     "gbd_pcg_plan_destroy", "gbd_pcg_plan_solve_host_f32", "gbd_pcg_plan_solve_host_f64",
     "gbd_pcg_launch_count", "gbd_pcg_set_debug_buffer", "gbd_schur_supported", "gbd_form_schur_system_f32",
-    "gbd_compute_dz_f32",
+    "gbd_compute_dz_f32", "gbd_step_plan_create", "gbd_step_plan_destroy", "gbd_step_run_f32", "gbd_step_results",
+    "gbd_step_device_flags",
 ]
 
 _lib = None
@@ -77,6 +78,16 @@ def lib():
     L.gbd_form_schur_system_f32.argtypes = [u32, u32, u32, vp, vp, vp, vp, vp, vp, vp, f32, vp]
     L.gbd_compute_dz_f32.restype = C.c_int
     L.gbd_compute_dz_f32.argtypes = [u32, u32, u32, vp, vp, vp, vp, vp, vp]
+    L.gbd_step_plan_create.restype = C.c_int
+    L.gbd_step_plan_create.argtypes = [u32, u32, u32, u32, C.POINTER(vp)]
+    L.gbd_step_plan_destroy.restype = C.c_int
+    L.gbd_step_plan_destroy.argtypes = [vp]
+    L.gbd_step_run_f32.restype = C.c_int
+    L.gbd_step_run_f32.argtypes = [vp, vp, vp, vp, vp, f32, vp, vp, u32, f32, vp]
+    L.gbd_step_results.restype = C.c_int
+    L.gbd_step_results.argtypes = [vp, vp, vp, vp]
+    L.gbd_step_device_flags.restype = vp
+    L.gbd_step_device_flags.argtypes = [vp]
     L.gbd_pcg_set_debug_buffer.restype = None
     L.gbd_pcg_set_debug_buffer.argtypes = [vp]
     _lib = L

@@ -538,15 +538,15 @@ int gbd_pcg_plan_solve_host_f64(gbd_pcg_plan *plan, const double *h_S, const dou
 
 namespace {
 template <uint32_t n, uint32_t m>
-int schur_launch(uint32_t N, float *G, const float *C, const float *g, const float *c, float *S, float *P, float *gam, float rho,
-                 cudaStream_t st)
+int schur_launch(uint32_t N, uint32_t batch, float *G, const float *C, const float *g, const float *c, float *S, float *P, float *gam,
+                 float rho, cudaStream_t st)
 {
     using K = gbd::SchurShape<n, m>;
-    gbd::schur_phase1_kernel<n, m><<<N, K::NT, K::P1_FLOATS * sizeof(float), st>>>(N, G, C, g, c, S, P, gam, rho);
+    gbd::schur_phase1_kernel<n, m><<<dim3(N, batch), K::NT, K::P1_FLOATS * sizeof(float), st>>>(N, G, C, g, c, S, P, gam, rho);
     {   // phase 2 with programmatic stream serialization: its launch overlaps phase 1, griddepcontrol.wait orders the data
         cudaLaunchConfig_t cfg = {};
         cudaLaunchAttribute at[1];
-        cfg.gridDim = dim3(N);
+        cfg.gridDim = dim3(N, batch);
         cfg.blockDim = dim3(K::NT);
         cfg.dynamicSmemBytes = K::P2_FLOATS * sizeof(float);
         cfg.stream = st;
@@ -562,9 +562,9 @@ int schur_launch(uint32_t N, float *G, const float *C, const float *g, const flo
     return GBD_PCG_OK;
 }
 template <uint32_t n, uint32_t m>
-int dz_launch(uint32_t N, const float *Gi, const float *C, const float *g, const float *lam, float *dz, cudaStream_t st)
+int dz_launch(uint32_t N, uint32_t batch, const float *Gi, const float *C, const float *g, const float *lam, float *dz, cudaStream_t st)
 {
-    gbd::compute_dz_kernel<n, m><<<N, 64, 0, st>>>(N, Gi, C, g, lam, dz);
+    gbd::compute_dz_kernel<n, m><<<dim3(N, batch), 64, 0, st>>>(N, Gi, C, g, lam, dz);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e);
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -589,7 +589,7 @@ int gbd_form_schur_system_f32(uint32_t n, uint32_t m, uint32_t N, float *d_G, co
                               const float *d_c, float *d_S, float *d_Pinv, float *d_gamma, float rho, void *stream)
 {
     if (!d_G || !d_C || !d_g || !d_c || !d_S || !d_Pinv || !d_gamma || N < 2) return GBD_PCG_ERR_BADARG;
-#define X(a, b) if (n == a && m == b) return schur_launch<a, b>(N, d_G, d_C, d_g, d_c, d_S, d_Pinv, d_gamma, rho, (cudaStream_t)stream);
+#define X(a, b) if (n == a && m == b) return schur_launch<a, b>(N, 1, d_G, d_C, d_g, d_c, d_S, d_Pinv, d_gamma, rho, (cudaStream_t)stream);
     GBD_SCHUR_SHAPES(X)
 #undef X
     return GBD_PCG_ERR_UNSUPPORTED;
@@ -599,11 +599,93 @@ int gbd_compute_dz_f32(uint32_t n, uint32_t m, uint32_t N, const float *d_Ginv, 
                        const float *d_lambda, float *d_dz, void *stream)
 {
     if (!d_Ginv || !d_C || !d_g || !d_lambda || !d_dz || N < 2) return GBD_PCG_ERR_BADARG;
-#define X(a, b) if (n == a && m == b) return dz_launch<a, b>(N, d_Ginv, d_C, d_g, d_lambda, d_dz, (cudaStream_t)stream);
+#define X(a, b) if (n == a && m == b) return dz_launch<a, b>(N, 1, d_Ginv, d_C, d_g, d_lambda, d_dz, (cudaStream_t)stream);
     GBD_SCHUR_SHAPES(X)
 #undef X
     return GBD_PCG_ERR_UNSUPPORTED;
 }
+
+}  // extern "C"
+
+// ---- f3: one SQP linear-system step (assembly -> PCG -> dz) for `batch` trajectories, enqueued without a host round trip
+struct gbd_step_plan {
+    uint32_t n, m, N, batch;
+    float *dS, *dP, *dgam;
+    uint32_t *d_iters;
+    uint8_t *d_flag;
+    uint32_t *h_iters;     // pinned
+    uint8_t *h_flag;       // pinned
+};
+
+extern "C" {
+
+int gbd_step_plan_create(uint32_t n, uint32_t m, uint32_t N, uint32_t batch, gbd_step_plan **out)
+{
+    if (!out || batch == 0 || N < 2) return GBD_PCG_ERR_BADARG;
+    if (!gbd_schur_supported(n, m) || !gbd_pcg_supported(n, N, 0)) return GBD_PCG_ERR_UNSUPPORTED;
+    gbd_step_plan *p = (gbd_step_plan *)calloc(1, sizeof(gbd_step_plan));
+    p->n = n; p->m = m; p->N = N; p->batch = batch;
+    const size_t mat = (size_t)3 * n * n * N * batch * sizeof(float), vec = (size_t)n * N * batch * sizeof(float);
+    cudaError_t e;
+    if ((e = cudaMalloc((void **)&p->dS, mat)) != cudaSuccess || (e = cudaMalloc((void **)&p->dP, mat)) != cudaSuccess ||
+        (e = cudaMalloc((void **)&p->dgam, vec)) != cudaSuccess ||
+        (e = cudaMalloc((void **)&p->d_iters, sizeof(uint32_t) * batch)) != cudaSuccess ||
+        (e = cudaMalloc((void **)&p->d_flag, batch)) != cudaSuccess ||
+        (e = cudaHostAlloc((void **)&p->h_iters, sizeof(uint32_t) * batch, cudaHostAllocDefault)) != cudaSuccess ||
+        (e = cudaHostAlloc((void **)&p->h_flag, batch, cudaHostAllocDefault)) != cudaSuccess) {
+        gbd_step_plan_destroy(p);
+        return cuda_fail(e);
+    }
+    // the pad tiles are never written by the assembly and never read by the solver; keep them defined
+    cudaMemset(p->dS, 0, mat);
+    cudaMemset(p->dP, 0, mat);
+    *out = p;
+    return GBD_PCG_OK;
+}
+
+int gbd_step_plan_destroy(gbd_step_plan *p)
+{
+    if (!p) return GBD_PCG_OK;
+    cudaFree(p->dS); cudaFree(p->dP); cudaFree(p->dgam); cudaFree(p->d_iters); cudaFree(p->d_flag);
+    if (p->h_iters) cudaFreeHost(p->h_iters);
+    if (p->h_flag) cudaFreeHost(p->h_flag);
+    free(p);
+    return GBD_PCG_OK;
+}
+
+int gbd_step_run_f32(gbd_step_plan *p, float *d_G, const float *d_C, const float *d_g, const float *d_c, float rho,
+                     float *d_lambda, float *d_dz, uint32_t max_iter, float exit_tol, void *stream)
+{
+    if (!p || !d_G || !d_C || !d_g || !d_c || !d_lambda || !d_dz) return GBD_PCG_ERR_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = GBD_PCG_ERR_UNSUPPORTED;
+#define X(a, b) if (p->n == a && p->m == b) rc = schur_launch<a, b>(p->N, p->batch, d_G, d_C, d_g, d_c, p->dS, p->dP, p->dgam, rho, st);
+    GBD_SCHUR_SHAPES(X)
+#undef X
+    if (rc) return rc;
+    rc = launch<float>(p->n, p->N, p->batch, p->dS, p->dP, p->dgam, d_lambda, (float *)nullptr, (float *)nullptr, p->d_iters, p->d_flag,
+                       max_iter, exit_tol, st);
+    if (rc) return rc;
+    rc = GBD_PCG_ERR_UNSUPPORTED;
+#define X(a, b) if (p->n == a && p->m == b) rc = dz_launch<a, b>(p->N, p->batch, d_G, d_C, d_g, d_lambda, d_dz, st);
+    GBD_SCHUR_SHAPES(X)
+#undef X
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(p->h_iters, p->d_iters, sizeof(uint32_t) * p->batch, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(p->h_flag, p->d_flag, p->batch, cudaMemcpyDeviceToHost, st));
+    return GBD_PCG_OK;
+}
+
+int gbd_step_results(gbd_step_plan *p, uint32_t *h_iters, uint8_t *h_flags, void *stream)
+{
+    if (!p) return GBD_PCG_ERR_BADARG;
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    if (h_iters) memcpy(h_iters, p->h_iters, sizeof(uint32_t) * p->batch);
+    if (h_flags) memcpy(h_flags, p->h_flag, p->batch);
+    return GBD_PCG_OK;
+}
+
+const uint8_t *gbd_step_device_flags(gbd_step_plan *p) { return p ? p->d_flag : nullptr; }
 
 void gbd_pcg_set_debug_buffer(void *d_buf) { g_dbg = (uint32_t *)d_buf; }
 

@@ -65,3 +65,26 @@ class ShardedBatch:
             solver.solve_batched(self.n, self.N, self.local, d_S, d_Pinv, d_gamma, d_lambda, self.iters, self.flags,
                                  max_iter, exit_tol)
         return gather_converged(self.flags[: self.local], self.batch, self.world, self.rank)
+
+
+class ShardedStep:
+    """This rank's shard of a batch of trajectories for the whole SQP linear-system step (KKT blocks in, dz out):
+    one StepPlan run on the local shard (assembly -> solve -> dz, no host round trip) + the one all-gather of the
+    per-trajectory max_iter_exit flags per outer step."""
+
+    def __init__(self, n: int, m: int, N: int, batch: int, world: int, rank: int):
+        from . import solver
+        self.n, self.m, self.N, self.batch, self.world, self.rank = n, m, N, batch, world, rank
+        self.lo, self.hi = shard_range(batch, world, rank)
+        self.local = self.hi - self.lo
+        self.plan = solver.StepPlan(n, m, N, self.local) if self.local else None
+
+    def step(self, d_G, d_C, d_g, d_c, rho, d_lambda, d_dz, max_iter: int, exit_tol: float):
+        """Returns the [batch] uint8 max_iter_exit vector of the whole batch (on this rank's GPU)."""
+        import torch
+        if self.plan is not None:
+            self.plan.run(d_G, d_C, d_g, d_c, rho, d_lambda, d_dz, max_iter, exit_tol)
+            flags = self.plan.device_flags()
+        else:
+            flags = torch.zeros(0, dtype=torch.uint8, device="cuda")
+        return gather_converged(flags, self.batch, self.world, self.rank)

@@ -199,3 +199,60 @@ def compute_dz(state_size, control_size, knot_points, d_G_dense, d_C_dense, d_g_
             raise ValueError(f"{name}: expected a contiguous CUDA float32 tensor of {want[name]} elements")
     _capi.check(_capi.lib().gbd_compute_dz_f32(n, m, N, _ptr(d_G_dense), _ptr(d_C_dense), _ptr(d_g_val), _ptr(d_lambda),
                                                _ptr(d_dz), _stream(stream)), "gbd_compute_dz_f32")
+
+
+class StepPlan:
+    """One SQP linear-system step for `batch` trajectories (gbd_step_*): form_schur_system -> pcg (warm-started) -> compute_dz
+    enqueued on one stream without a host round trip; mirrors include/pcg/sqp.cuh:207-258 per SQP iteration.  The plan owns
+    S, Pinv, gamma and the result slots."""
+
+    def __init__(self, state_size: int, control_size: int, knot_points: int, batch: int = 1):
+        import ctypes as C
+        self.n, self.m, self.N, self.batch = state_size, control_size, knot_points, batch
+        h = C.c_void_p()
+        _capi.check(_capi.lib().gbd_step_plan_create(state_size, control_size, knot_points, batch, C.byref(h)), "gbd_step_plan_create")
+        self._h = h
+
+    def sizes(self):
+        n, m, N, B = self.n, self.m, self.N, self.batch
+        return dict(G=B * ((n * n + m * m) * (N - 1) + n * n), C=B * (n * n + n * m) * (N - 1), g=B * ((n + m) * (N - 1) + n),
+                    c=B * n * N, lam=B * n * N, dz=B * ((n + m) * (N - 1) + n))
+
+    def run(self, d_G, d_C, d_g, d_c, rho, d_lambda, d_dz, max_iter, exit_tol, stream=None):
+        """Asynchronous.  d_G is overwritten with the block inverses; d_lambda is in/out; d_dz is written."""
+        import torch
+        sz = self.sizes()
+        for name, t, key in (("d_G", d_G, "G"), ("d_C", d_C, "C"), ("d_g", d_g, "g"), ("d_c", d_c, "c"), ("d_lambda", d_lambda, "lam"),
+                             ("d_dz", d_dz, "dz")):
+            if not t.is_cuda or not t.is_contiguous() or t.dtype != torch.float32 or t.numel() != sz[key]:
+                raise ValueError(f"{name}: expected a contiguous CUDA float32 tensor of {sz[key]} elements")
+        _capi.check(_capi.lib().gbd_step_run_f32(self._h, _ptr(d_G), _ptr(d_C), _ptr(d_g), _ptr(d_c), float(rho), _ptr(d_lambda),
+                                                 _ptr(d_dz), int(max_iter), float(exit_tol), _stream(stream)), "gbd_step_run_f32")
+
+    def results(self, stream=None):
+        """Blocks on the stream; returns (iters[batch] uint32, max_iter_exit[batch] uint8) of the last run."""
+        import numpy as np
+        it = np.zeros(self.batch, np.uint32)
+        fl = np.zeros(self.batch, np.uint8)
+        _capi.check(_capi.lib().gbd_step_results(self._h, it.ctypes.data, fl.ctypes.data, _stream(stream)), "gbd_step_results")
+        return it, fl
+
+    def device_flags(self):
+        """[batch] uint8 CUDA tensor view of the max_iter_exit flags of the last run (what the multi-GPU driver all-gathers)."""
+        import torch
+        ptr = _capi.lib().gbd_step_device_flags(self._h)
+
+        class _Arr:
+            __cuda_array_interface__ = {"shape": (self.batch,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+        return torch.as_tensor(_Arr(), device="cuda")
+
+    def close(self):
+        if self._h:
+            _capi.lib().gbd_step_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -100,3 +100,33 @@ def bytes_per_iteration(n: int, N: int, elem: int = 4) -> int:
 
 def flops_per_iteration(n: int, N: int) -> int:
     return 2 * 2 * (3 * N - 2) * n * n + 10 * N * n
+
+
+def make_kkt_batch(n: int, m: int, N: int, batch: int = 1, seed: int = 0, chunk: int = 64):
+    """Seeded synthetic KKT blocks for `batch` trajectories in the reference's dense layouts (the inputs of form_schur_system,
+    include/pcg/linsys_setup.cuh:621-657): G = per knot [Q_k (n*n) | R_k (m*m)] (last knot Q only), C = per knot
+    [A_k (n*n) | B_k (n*m)], g = per knot [q_k | r_k], c = n per knot; blocks column-major.  SPD Q, R; A = I + small; B small.
+    Returns float32 arrays G [batch, .], C [batch, .], g [batch, .], c [batch, .]."""
+    rng = np.random.default_rng(seed)
+    nn, mm, nm = n * n, m * m, n * m
+    G = np.empty((batch, (nn + mm) * (N - 1) + nn), np.float32)
+    C = np.empty((batch, (nn + nm) * (N - 1)), np.float32)
+    g = np.empty((batch, (n + m) * (N - 1) + n), np.float32)
+    c = np.empty((batch, n * N), np.float32)
+    for b0 in range(0, batch, chunk):
+        B = min(chunk, batch - b0)
+        M = rng.standard_normal((B, N, n, n))
+        Q = M @ np.swapaxes(M, -1, -2) / n + np.eye(n)
+        Mr = rng.standard_normal((B, N - 1, m, m))
+        R = Mr @ np.swapaxes(Mr, -1, -2) / m + np.eye(m)
+        A = np.eye(n) + rng.standard_normal((B, N - 1, n, n)) / 16
+        Bm = rng.standard_normal((B, N - 1, n, m)) / 16
+        q = rng.standard_normal((B, N, n))
+        r = rng.standard_normal((B, N - 1, m))
+        Gk = np.concatenate([np.swapaxes(Q[:, :-1], -1, -2).reshape(B, N - 1, nn), np.swapaxes(R, -1, -2).reshape(B, N - 1, mm)], axis=2)
+        G[b0:b0 + B] = np.concatenate([Gk.reshape(B, -1), np.swapaxes(Q[:, -1], -1, -2).reshape(B, nn)], axis=1)
+        C[b0:b0 + B] = np.concatenate([np.swapaxes(A, -1, -2).reshape(B, N - 1, nn), np.swapaxes(Bm, -1, -2).reshape(B, N - 1, nm)],
+                                      axis=2).reshape(B, -1)
+        g[b0:b0 + B] = np.concatenate([np.concatenate([q[:, :-1], r], axis=2).reshape(B, -1), q[:, -1]], axis=1)
+        c[b0:b0 + B] = 0.1 * rng.standard_normal((B, n * N))
+    return G, C, g, c

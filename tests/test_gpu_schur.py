@@ -139,3 +139,34 @@ def test_form_schur_and_dz_on_reference_minted_iiwa_vectors(torch_cuda):
         assert int(it.item()) == int(z["pcg_iters"])
         assert np.array_equal(lam.cpu().numpy(), z["lam"])
         assert np.array_equal(dz.cpu().numpy(), z["dz"])
+
+
+@pytest.mark.parametrize("n,m,N,B", [(14, 7, 32, 5), (14, 7, 128, 3)])
+def test_batched_step_plan_equals_per_system_oracle_chain(torch_cuda, n, m, N, B):
+    """gbd_step_run_f32 (row f3): assembly -> warm-started solve -> dz for a batch, one enqueue; every trajectory equals the
+    oracle chain bit for bit, and the flags the multi-GPU driver gathers are the per-trajectory max_iter_exit."""
+    torch = torch_cuda
+    import mpcgpu_b200 as mp
+    from mpcgpu_b200 import sharding
+    from oracle import pcg as opcg
+    from oracle import schur
+    kk = [schur.make_kkt(n, m, N, seed=300 + i) for i in range(B)]
+    G, C, g, c = (np.concatenate([k[j] for k in kk]) for j in range(4))
+    lam0 = (0.01 * np.random.default_rng(3).standard_normal(B * n * N)).astype(np.float32)
+    dG, dC, dg, dc, dl = (torch.from_numpy(x.copy()).cuda() for x in (G, C, g, c, lam0))
+    dz = torch.zeros(B * ((n + m) * (N - 1) + n), device="cuda")
+    plan = mp.StepPlan(n, m, N, B)
+    cap, tol = 30, 1e-5                                   # a cap some trajectories hit, so both flag values occur
+    plan.run(dG, dC, dg, dc, 1e-3, dl, dz, cap, tol)
+    it, fl = plan.results()
+    flags_dev = plan.device_flags().cpu().numpy()
+    gathered = sharding.gather_converged(plan.device_flags(), B, 1, 0).cpu().numpy()
+    nl, nz = n * N, (n + m) * (N - 1) + n
+    for i in range(B):
+        o = schur.form(kk[i][0], kk[i][1], kk[i][2], kk[i][3], n, m, N, 1e-3)
+        w = opcg.pcg(o["S"], o["Pinv"], o["gamma"], lam0[i * nl:(i + 1) * nl], n, N, cap, tol)
+        assert int(it[i]) == w["iters"] and bool(fl[i]) == w["max_iter_exit"], i
+        assert np.array_equal(dl.cpu().numpy()[i * nl:(i + 1) * nl], w["lam"]), i
+        assert np.array_equal(dz.cpu().numpy()[i * nz:(i + 1) * nz], schur.dz(o["Ginv"], kk[i][1], kk[i][2], w["lam"], n, m, N)), i
+    assert np.array_equal(flags_dev, fl) and np.array_equal(gathered, fl)
+    plan.close()
