@@ -111,7 +111,7 @@ def main():
             lam.zero_()
             m.solve_batched(n, N, B, S, P, g, lam, it, fl, cap, tol)
 
-        for v in [v for v in _capi.variants() if v["n"] == n and v["N"] == N and not v["f64"] and v["mode"] in (MODES or (2, 3, 5, 6, 7, 8))]:
+        for v in [v for v in _capi.variants() if v["n"] == n and v["N"] == N and not v["f64"] and v["mode"] in (MODES or (2, 3, 5, 6, 7, 8, 11, 12, 13))]:
             assert L.gbd_pcg_set_tuning(n, N, 0, v["cluster"], v["mode"]) == 0
             us = time_fn(batched, 5, warm=2)
             out.append(dict(impl="ours_batched", n=n, N=N, batch=B, cluster=v["cluster"], mode=v["mode"], ms=us / 1e3,
