@@ -209,6 +209,14 @@ def run_reference_arm(args):
         nb = max(1, 16 * ncores // 64 + 1) * 64
         extra["batched"] = {"traj_per_sec": nb / secb, "cores": ncores,
                             "sample": f"{nb} independent QDLDL solves over {ncores} threads"}
+        # BASELINE.json configs[0]: the reference's own CPU-runnable case (knot_points = 32, include/qdldl/sqp.cuh:22-49)
+        s32 = synth.make_systems(N_STATE, 32, batch=64, seed=2025)
+        v32 = qdldl.values(s32["S"], N_STATE, 32)
+        t1, _ = qdldl.time_batched(v32, s32["gamma"], N_STATE, 32, reps=1, nthreads=1)
+        r32 = max(1, int(1.0 / max(t1, 1e-6)))
+        t32, _ = qdldl.time_batched(v32, s32["gamma"], N_STATE, 32, reps=r32, nthreads=1)
+        extra["config0_n32"] = {"us_per_solve": 1e6 * t32 / (r32 * 64), "solves_per_sec": r32 * 64 / t32, "cores": 1,
+                                "sample": f"{r32 * 64} QDLDL factor+solve pairs, n=14 N=32, 1 thread"}
     line = {
         "impl": "reference", "metric": "linsys_solves_per_sec", "value": value, "unit": "solves/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps,
