@@ -111,9 +111,11 @@ __device__ __forceinline__ T glass_tree_part(const T *part)
                 if (q < h) v[q] = add_rn(v[q], v[q + h]);
         }
         T x = v[0];
+        // XOR butterfly: lane l < s adds the same pair as the halving tree does (a + b == b + a bit for bit), and every
+        // lane ends with the total -- no broadcast shuffle
 #pragma unroll
-        for (uint32_t s = 16; s >= 1; s /= 2) x = add_rn(x, __shfl_down_sync(0xffffffffu, x, s));
-        return __shfl_sync(0xffffffffu, x, 0);
+        for (uint32_t s = 16; s >= 1; s /= 2) x = add_rn(x, __shfl_xor_sync(0xffffffffu, x, s));
+        return x;
     } else {
         T v[CNT];
 #pragma unroll
