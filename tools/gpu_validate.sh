@@ -1,5 +1,5 @@
 #!/bin/bash
-# full validation + bench + ncu evidence for this session (r01c)
+# full validation + bench + ncu evidence (produces the profiles/r01c_* files)
 mkdir -p gpurun_out
 echo "== smoke"; timeout -k 5 180 python __graft_entry__.py smoke 2>&1 | tail -2 | tee gpurun_out/smoke.log
 echo "== pytest gpu"; timeout -k 5 900 python -m pytest tests -m gpu -q -x --timeout=300 2>&1 | tail -5 | tee gpurun_out/pytest_gpu.log
