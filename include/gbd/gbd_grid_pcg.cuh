@@ -108,7 +108,8 @@ __device__ __forceinline__ T chain_padded_smem(const T *__restrict__ mrow, const
     constexpr uint32_t CB = 4 * V;                       // columns per register block of the window
 #pragma unroll
     for (uint32_t blk = 0; blk < 3; ++blk) {
-#pragma unroll 1
+        // fully unrolled: the matrix loads of later column blocks are issued while the FMA chain of the current one runs
+#pragma unroll
         for (uint32_t c0 = 0; c0 + CB <= n; c0 += CB) {
             T x[CB];
 #pragma unroll
