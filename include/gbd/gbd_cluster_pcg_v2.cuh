@@ -177,7 +177,7 @@ __device__ __forceinline__ T chain_padded(const T (&m)[3 * n], const T *__restri
     return acc;
 }
 
-template <typename T, uint32_t n, uint32_t N, uint32_t C, uint32_t MINB>
+template <typename T, uint32_t n, uint32_t N, uint32_t C, uint32_t MINB, bool PROF = false>
 __global__ void __launch_bounds__(ClusterPcg2<T, n, N, C>::NT, MINB)
 pcg_cluster_kernel_v2(const PcgArgs<T> a)
 {
@@ -350,20 +350,36 @@ pcg_cluster_kernel_v2(const PcgArgs<T> a)
 
         uint32_t iter = 0;
         uint8_t max_iter_exit = 1;
+        // timeline build (mode 14): %clock stamps of iterations 8..11, [iter][point][thread] (tools/timeline.py)
+        auto stamp = [&](uint32_t pt, T dep) {
+            if constexpr (PROF) {
+                if (a.dbg && iter >= 8 && iter < 12) {
+                    uint32_t c_;
+                    asm volatile("mov.u32 %0, %%clock;" : "=r"(c_) : "f"((float)dep) : "memory");
+                    a.dbg[((iter - 8) * 12 + pt) * (C * NT) + cr * NT + t] = c_;
+                }
+            }
+        };
         for (; iter < a.max_iter; ++iter) {
             __syncthreads();
+            stamp(0, p);
             // ---- upsilon = S*p ; v = p.upsilon                             (pcg.cuh:156-167)
             ups = chain_padded<T, n, XS>(ms, wp);
+            stamp(1, ups);
             {
                 const T x = glass_tree_shfl<T, n, G>(mul_rn(p, ups), j);
                 if (group_live && j == 0) part_v[b] = x;
+                stamp(2, x);
             }
             if (own_lhalo) hs[j] = ups;
             if (own_rhalo) hs[XS + j] = ups;
             ship(part_v, barA, hu + XS, hu, true, full_bytes);
+            stamp(3, ups);
             mbar_wait(barA, phA);
             phA ^= 1u;
+            stamp(4, ups);
             const T alpha = eta / glass_tree_part<T, N>(part_v);               // :169
+            stamp(5, alpha);
             // ---- lambda += alpha p ; r -= alpha upsilon (own rows + halo copies)   (:172-176)
             lam = fma_rn(alpha, p, lam);
             r = fma_rn(-alpha, ups, r);
@@ -371,8 +387,10 @@ pcg_cluster_kernel_v2(const PcgArgs<T> a)
             if (own_lhalo && has_left) xr[j] = fma_rn(-alpha, hu[j], xr[j]);
             if (own_rhalo && has_right) xr[(R + 1) * XS + j] = fma_rn(-alpha, hu[XS + j], xr[(R + 1) * XS + j]);
             __syncthreads();
+            stamp(6, r);
             // ---- r~ = Pinv*r ; eta' = r.r~                                 (:180-193)
             rt = chain_padded<T, n, XS>(mp, wr);
+            stamp(7, rt);
             {
                 const T x = glass_tree_shfl<T, n, G>(mul_rn(r, rt), j);
                 if (group_live && j == 0) part_e[b] = x;
@@ -380,9 +398,12 @@ pcg_cluster_kernel_v2(const PcgArgs<T> a)
             if (own_lhalo) hs[j] = rt;
             if (own_rhalo) hs[XS + j] = rt;
             ship(part_e, barB, ht + XS, ht, true, full_bytes);
+            stamp(8, rt);
             mbar_wait(barB, phB);
             phB ^= 1u;
+            stamp(9, rt);
             const T eta_new = glass_tree_part<T, N>(part_e);
+            stamp(10, eta_new);
             if (abs_(eta_new) < a.exit_tol) { ++iter; max_iter_exit = 0; break; }   // :195
             const T beta = eta_new / eta;                                       // :199-200
             eta = eta_new;

@@ -28,6 +28,7 @@ using namespace gbd;
 //       5 = v3 kernel (two matrix rows per thread, 8-lane knot rows), 1 CTA/SM register budget; 6 = v3, 2 CTAs/SM
 //       7 = v4 kernel (self-validating packets polled in shared memory, register N-way tree), 1 CTA/SM; 8 = v4, 2 CTAs/SM
 //      11 = v5 kernel (v3's two-rows-per-thread mapping + v4's packet exchange), 1 CTA/SM; 12 = v5, 2 CTAs/SM
+//      14 = v2 timeline build (same stamps as mode 10)
 //      10 = v4 timeline build: per-thread %clock stamps of iterations 8..11 into gbd_pcg_set_debug_buffer()
 struct Variant {
     uint32_t n, N, C;
@@ -54,6 +55,13 @@ Variant make_v2()
     using K = ClusterPcg2<T, n, N, C>;
     return Variant{n, N, C, MINB == 1 ? 2 : 3, sizeof(T) == 8, K::NT, K::SMEM_BYTES,
                    (const void *)pcg_cluster_kernel_v2<T, n, N, C, MINB>, false, 0};
+}
+
+template <uint32_t n, uint32_t N, uint32_t C>
+Variant make_v2_prof()
+{
+    using K = ClusterPcg2<float, n, N, C>;
+    return Variant{n, N, C, 14, false, K::NT, K::SMEM_BYTES, (const void *)pcg_cluster_kernel_v2<float, n, N, C, 1, true>, false, 0};
 }
 
 template <uint32_t n, uint32_t N, uint32_t C, uint32_t MINB>
@@ -128,6 +136,7 @@ std::vector<Variant> &variants()
         make_v5<14, 128, 4, 1>(),                 make_v5<14, 64, 4, 1>(),
         make_v5<14, 64, 8, 1>(),                  make_v5<14, 32, 2, 1>(),
         make_v5<14, 32, 4, 1>(),                  make_v5<14, 256, 8, 1>(),
+        make_v2_prof<14, 128, 16>(),              make_v2_prof<14, 128, 8>(),
         make_v4<14, 128, 16, 1, false, true>(),   make_v4<14, 128, 8, 1, false, true>(),
         make_v4<14, 32, 4, 1, false, true>(),     make_v4<14, 64, 8, 1, false, true>(),
         make_variant<float, 14, 128, 8, true>(),  make_variant<float, 14, 128, 16, true>(),
