@@ -33,51 +33,52 @@ namespace schur_detail {
 
 __device__ __forceinline__ float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 
-// Gauss-Jordan on [V | I] (DIM x 2 DIM, column-major) by ONE warp.  Per pivot p the reference updates the DIM+1
-// columns p .. p+DIM from a snapshot of the pivot column `col` and pivot row `rowv`:
+// Gauss-Jordan on [V | I] (DIM x 2 DIM) by ONE warp with the matrix rows in REGISTERS: lane r < DIM holds row r of the
+// augmented matrix (2 DIM values, the identity half generated in place), the pivot loop is fully unrolled so every
+// register index is static.  Per pivot p the reference updates the DIM+1 columns p .. p+DIM from a snapshot of the
+// pivot column `col` and pivot row `rowv`:
 //   several-matrices form (matrix.cuh:149-238, DIV = true):  row == p : x / piv      else : fma(-(col[row] / piv), rowv[c], x)
 //   single-matrix form    (matrix.cuh:120-146, DIV = false): pvInv = 1 / piv;
 //                                                            row == p : x * pvInv    else : fma(-(col[row] * pvInv), rowv[c], x)
-// Here every division of a pivot step is issued at once in step (a): lanes 0..DIM-1 form the row factors col[row]/piv
-// (resp. col[row]*pvInv), lanes 16.. the new pivot row; step (b) is then one FMA per element with all of a lane's
-// elements in flight together.  Same operands and operations per element as the reference -> same bits.
+// Here: lane p publishes its window row through shared memory; ONE division sequence serves both kinds of quotient
+// (lanes 0..DIM-1 form their own row factor col[row]/piv from a register, lanes 16..16+DIM the new pivot-row element
+// rowv[c]/piv); then one FMA per element.  Same operands and operations per element as the reference -> same bits,
+// with ~2x fewer instructions and half the dependent latency of the shared-memory-resident version.
+// A: in shared memory, V (DIM x DIM, column-major) followed by DIM x DIM floats that receive V^-1.  snap: 32 floats, 16-B aligned.
 template <uint32_t DIM, bool DIV>
 __device__ __forceinline__ void gj_warp(float *A, float *snap, uint32_t lane)
 {
-    static_assert(DIM + 1 <= 16, "one warp: factors in lanes 0..15, pivot row in lanes 16..31");
-    float *rowv = snap, *f = snap + (DIM + 1), *nrow = f + DIM;      // DIM+1, DIM, DIM+1 floats
-    constexpr uint32_t ELEMS = DIM * (DIM + 1), PER = (ELEMS + 31) / 32;
+    static_assert(DIM + 1 <= 16, "one warp: row factors in lanes 0..15, new pivot row in lanes 16..31");
+    float *row = snap, *nrow = snap + 16;
+    const uint32_t r = lane < DIM ? lane : 0;            // lanes DIM..15 and 16.. shadow row 0 (never stored)
+    const uint32_t cI = lane >= 16 ? (lane - 16 <= DIM ? lane - 16 : 0) : 0;
+    float a[2 * DIM];
+#pragma unroll
+    for (uint32_t c = 0; c < DIM; ++c) {
+        a[c] = A[c * DIM + r];
+        a[DIM + c] = (c == r) ? 1.0f : 0.0f;
+    }
+#pragma unroll
     for (uint32_t p = 0; p < DIM; ++p) {
-        const uint32_t off = p * DIM;
-        const float piv = A[p + off];
-        // ---- (a) snapshot + all divisions of this pivot step
-        if (lane < DIM) {
-            const float cv = A[lane + off];
-            f[lane] = DIV ? __fdiv_rn(cv, piv) : __fmul_rn(cv, __fdiv_rn(1.0f, piv));
-        } else if (lane >= 16 && lane < 16 + DIM + 1) {
-            const uint32_t cI = lane - 16;
-            const float rv = A[cI * DIM + p + off];
-            rowv[cI] = rv;
-            nrow[cI] = DIV ? __fdiv_rn(rv, piv) : __fmul_rn(rv, __fdiv_rn(1.0f, piv));
+        if (lane == p) {
+#pragma unroll
+            for (uint32_t c = 0; c <= DIM; ++c) row[c] = a[p + c];
         }
         __syncwarp();
-        // ---- (b) one FMA per element, all of this lane's elements in flight together
-        float x[PER];
+        const float piv = row[0];
+        const float num = lane < 16 ? a[p] : row[cI];
+        const float q = DIV ? __fdiv_rn(num, piv) : __fmul_rn(num, __fdiv_rn(1.0f, piv));
+        if (lane >= 16 && lane - 16 <= DIM) nrow[cI] = q;
+        __syncwarp();
 #pragma unroll
-        for (uint32_t q = 0; q < PER; ++q) {
-            const uint32_t ind = lane + 32 * q;
-            x[q] = ind < ELEMS ? A[off + ind] : 0.0f;
-        }
-#pragma unroll
-        for (uint32_t q = 0; q < PER; ++q) {
-            const uint32_t ind = lane + 32 * q;
-            if (ind < ELEMS) {
-                const uint32_t row = ind % DIM, col = ind / DIM;
-                A[off + ind] = (row == p) ? nrow[col] : fma_(-f[row], rowv[col], x[q]);
-            }
-        }
+        for (uint32_t c = 0; c <= DIM; ++c) a[p + c] = (lane == p) ? nrow[c] : fma_(-q, row[c], a[p + c]);
         __syncwarp();
     }
+    if (lane < DIM) {
+#pragma unroll
+        for (uint32_t c = 0; c < DIM; ++c) A[(DIM + c) * DIM + lane] = a[DIM + c];
+    }
+    __syncwarp();
 }
 template <uint32_t DIM>
 __device__ __forceinline__ void gj_div_warp(float *A, float *snap, uint32_t lane) { gj_warp<DIM, true>(A, snap, lane); }
@@ -115,7 +116,7 @@ struct SchurShape {
     static constexpr uint32_t GSET = nn + mm, CSET = nn + nm;
     // phase-1 shared memory (floats)
     static constexpr uint32_t P1_FLOATS = nn /*A*/ + nm /*B*/ + 2 * nn /*Qk|I*/ + 2 * nn /*Qkp1|I*/ + 2 * mm /*R|I*/ + nn /*phi*/ + nm /*BR*/ +
-                                          2 * nn /*theta|I*/ + nn /*BRBt*/ + 6 * n + m + 3 * (3 * n + 2);   // 3 snapshots: pivot row, row factors, new pivot row
+                                          2 * nn /*theta|I*/ + nn /*BRBt*/ + 6 * n + m + 3 + 3 * 32;   // + alignment slack + 3 pivot-row snapshots
     static constexpr uint32_t P2_FLOATS = 7 * nn;
 };
 
@@ -133,7 +134,8 @@ schur_phase1_kernel(uint32_t N, const float *__restrict__ G, const float *__rest
     float *sA = sm, *sB = sA + nn, *sQk = sB + nm, *sQk_i = sQk + nn, *sQp = sQk_i + nn, *sQp_i = sQp + nn;
     float *sR = sQp_i + nn, *sR_i = sR + mm, *sPhi = sR_i + mm, *sBR = sPhi + nn, *sTh = sBR + nm, *sTh_i = sTh + nn;
     float *sBRBt = sTh_i + nn, *sqk = sBRBt + nn, *sqp = sqk + n, *srk = sqp + n, *sgam = srk + m, *sx0 = sgam + n, *sx1 = sx0 + n;
-    float *sc = sx1 + n, *snap = sc + n;                      // 3 snapshots of 3n+2 floats
+    float *sc = sx1 + n;
+    float *snap = sm + ((sc + n - sm) + 3) / 4 * 4;              // 3 snapshots of 32 floats, 16-byte aligned
     const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5, b = blockIdx.x;
     {   // blockIdx.y = system of a batch: every array carries a leading [batch] dimension
         const size_t sys = blockIdx.y;
@@ -145,7 +147,6 @@ schur_phase1_kernel(uint32_t N, const float *__restrict__ G, const float *__rest
     if (b == 0) {
         // ---- leading block (:151-278): Pinv_00 = -(Q_0 + rho I), S_00 = -Q_0^-1, gamma_0 = -Q_0^-1 q_0
         for (uint32_t i = t; i < nn; i += NT) sQk[i] = (i % n == i / n) ? __fadd_rn(G[i], rho) : G[i];
-        identity(sQk_i, n, t, NT);
         for (uint32_t i = t; i < n; i += NT) sqk[i] = g[i];
         __syncthreads();
         for (uint32_t i = t; i < nn; i += NT) Prow[nn + i] = sQk[i] * -1.0f;
@@ -172,14 +173,11 @@ schur_phase1_kernel(uint32_t N, const float *__restrict__ G, const float *__rest
         sc[i] = c[(size_t)b * n + i];
     }
     for (uint32_t i = t; i < m; i += NT) srk[i] = g[(size_t)(b - 1) * (n + m) + n + i];
-    identity(sQk_i, n, t, NT);
-    identity(sQp_i, n, t, NT);
-    identity(sR_i, m, t, NT);
     __syncthreads();
     // ---- the three inversions side by side, one warp each (:351-363)
     if (warp == 0) gj_div_warp<n>(sQk, snap, lane);
-    else if (warp == 1) gj_div_warp<n>(sQp, snap + (3 * n + 2), lane);
-    else if (warp == 2) gj_div_warp<m>(sR, snap + 2 * (3 * n + 2), lane);
+    else if (warp == 1) gj_div_warp<n>(sQp, snap + 32, lane);
+    else if (warp == 2) gj_div_warp<m>(sR, snap + 64, lane);
     __syncthreads();
     // park the inverses for compute_dz in tiles that phase 2 overwrites (moved into G there): Q_{b-1}^-1 in the left
     // tile of row b, R_{b-1}^-1 in the right tile of row b-1, Q_{N-1}^-1 in the pad tile (left of row 0)
@@ -214,7 +212,6 @@ schur_phase1_kernel(uint32_t N, const float *__restrict__ G, const float *__rest
         const float gm = __fadd_rn(__fadd_rn(sgam[i], -sc[i]), __fadd_rn(sx1[i], sx0[i]));
         gamma[(size_t)b * n + i] = gm * -1.0f;
     }
-    identity(sTh_i, n, t, NT);
     __syncthreads();
     // ---- theta^-1 (:503-518)
     if (warp == 0) gj_rcp_warp<n>(sTh, snap, lane);
