@@ -306,4 +306,40 @@ compute_dz_kernel(uint32_t N, const float *__restrict__ Ginv, const float *__res
     }
 }
 
+// ---- row f4 (wire format): the band S -> upper-triangular CSC of the symmetric block-tridiagonal matrix, the format the
+// reference hands to QDLDL (include/utils/csr.cuh:10-74: prep_csr builds col_ptr / row_ind, store_block_csr_lowertri the
+// values; include/qdldl/sqp.cuh:148,164).  Column j = (block row b, row r) holds rows (b-1)n .. (b-1)n+n-1 (row r of the left
+// tile) then rows bn .. bn+r (row r of the diagonal tile up to the diagonal).  Pure index work: bit-exact by construction.
+__host__ __device__ inline uint32_t csr_nnz(uint32_t n, uint32_t N) { return (N - 1) * n * n + N * ((n + 1) * n / 2); }
+__host__ __device__ inline uint32_t csr_col_offset(uint32_t n, uint32_t b, uint32_t r)
+{
+    const uint32_t tri = (n + 1) * n / 2, brow = n * n + tri;
+    return (b > 0 ? tri + (b - 1) * brow + r * n : 0u) + (r + 1) * r / 2;
+}
+__global__ void __launch_bounds__(64)
+csr_pattern_kernel(uint32_t n, uint32_t N, int32_t *__restrict__ col_ptr, int32_t *__restrict__ row_ind)
+{
+    for (uint32_t b = blockIdx.x; b < N; b += gridDim.x)
+        for (uint32_t r = threadIdx.x; r < n; r += blockDim.x) {
+            if (b == 0 && r == 0) col_ptr[0] = 0;
+            const uint32_t off = csr_col_offset(n, b, r), len = (b > 0 ? n : 0u) + r + 1;
+            col_ptr[b * n + r + 1] = (int32_t)(off + len);
+            for (uint32_t c = 0; c < len; ++c) row_ind[off + c] = (int32_t)((b > 0 ? (b - 1) * n : 0u) + c);
+        }
+}
+__global__ void __launch_bounds__(128)
+csr_values_kernel(uint32_t n, uint32_t N, const float *__restrict__ S, float *__restrict__ val)
+{
+    const uint32_t b = blockIdx.x;
+    const float *L = S + (size_t)b * 3 * n * n, *D = L + n * n;
+    // one (row, col) element per thread iteration; consecutive threads walk a column of the tile (coalesced reads)
+    for (uint32_t e = threadIdx.x; e < 2 * n * n; e += blockDim.x) {
+        const bool diag = e >= n * n;
+        const uint32_t q = diag ? e - n * n : e, r = q % n, c = q / n;
+        const uint32_t off = csr_col_offset(n, b, r);
+        if (!diag) { if (b > 0) val[off + c] = L[r + c * n]; }
+        else if (c <= r) val[off + (b > 0 ? n : 0u) + c] = D[r + c * n];
+    }
+}
+
 }  // namespace gbd

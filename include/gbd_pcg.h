@@ -156,6 +156,16 @@ int gbd_step_run_f32(gbd_step_plan *plan, float *d_G, const float *d_C, const fl
 int gbd_step_results(gbd_step_plan *plan, uint32_t *h_iters, uint8_t *h_max_iter_exit, void *stream);
 const uint8_t *gbd_step_device_flags(gbd_step_plan *plan);
 
+/*
+ * The QDLDL wire format of the band matrix (include/utils/csr.cuh:10-74): upper-triangular CSC of the
+ * symmetric block-tridiagonal S, what the reference's CPU path (include/qdldl/sqp.cuh:148-198,268-273) factorises.
+ * gbd_schur_csr_pattern_i32 replaces prep_csr (col_ptr: n*N+1 ints, row_ind: nnz ints); gbd_schur_csr_values_f32 packs the
+ * left and diagonal tiles of d_S ([N][3][n][n], the pcg<> layout) as store_block_csr_lowertri does (nnz floats).
+ */
+uint32_t gbd_schur_csr_nnz(uint32_t n, uint32_t N);
+int gbd_schur_csr_pattern_i32(uint32_t n, uint32_t N, int32_t *d_col_ptr, int32_t *d_row_ind, void *stream);
+int gbd_schur_csr_values_f32(uint32_t n, uint32_t N, const float *d_S, float *d_val, void *stream);
+
 /* Number of kernels this library has launched in this process (for bench.py's gpu_launches). */
 uint64_t gbd_pcg_launch_count(void);
 

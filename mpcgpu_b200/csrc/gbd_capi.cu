@@ -722,6 +722,29 @@ int gbd_step_results(gbd_step_plan *p, uint32_t *h_iters, uint8_t *h_flags, void
 
 const uint8_t *gbd_step_device_flags(gbd_step_plan *p) { return p ? p->d_flag : nullptr; }
 
+// ---- f4: the QDLDL wire format of the band matrix (include/utils/csr.cuh)
+uint32_t gbd_schur_csr_nnz(uint32_t n, uint32_t N) { return gbd::csr_nnz(n, N); }
+
+int gbd_schur_csr_pattern_i32(uint32_t n, uint32_t N, int32_t *d_col_ptr, int32_t *d_row_ind, void *stream)
+{
+    if (!d_col_ptr || !d_row_ind || N < 1 || n < 1) return GBD_PCG_ERR_BADARG;
+    gbd::csr_pattern_kernel<<<N, 64, 0, (cudaStream_t)stream>>>(n, N, d_col_ptr, d_row_ind);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return GBD_PCG_OK;
+}
+
+int gbd_schur_csr_values_f32(uint32_t n, uint32_t N, const float *d_S, float *d_val, void *stream)
+{
+    if (!d_S || !d_val || N < 1 || n < 1) return GBD_PCG_ERR_BADARG;
+    gbd::csr_values_kernel<<<N, 128, 0, (cudaStream_t)stream>>>(n, N, d_S, d_val);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return GBD_PCG_OK;
+}
+
 void gbd_pcg_set_debug_buffer(void *d_buf) { g_dbg = (uint32_t *)d_buf; }
 
 uint64_t gbd_pcg_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

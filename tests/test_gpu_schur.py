@@ -170,3 +170,48 @@ def test_batched_step_plan_equals_per_system_oracle_chain(torch_cuda, n, m, N, B
         assert np.array_equal(dz.cpu().numpy()[i * nz:(i + 1) * nz], schur.dz(o["Ginv"], kk[i][1], kk[i][2], w["lam"], n, m, N)), i
     assert np.array_equal(flags_dev, fl) and np.array_equal(gathered, fl)
     plan.close()
+
+
+@pytest.mark.parametrize("n,N", [(14, 32), (14, 128), (6, 12), (2, 3)])
+def test_csr_wire_format_bit_exact_and_feeds_qdldl(torch_cuda, n, N):
+    """Row f4: band S -> upper-triangular CSC (include/utils/csr.cuh:10-74).  Index/byte work: identical to the oracle's
+    restatement; and the reference's own QDLDL, fed with the GPU-packed matrix, agrees with the GPU PCG solution."""
+    torch = torch_cuda
+    import mpcgpu_b200 as mp
+    from mpcgpu_b200 import _capi, synth
+    from oracle import qdldl
+    if not qdldl.available():
+        pytest.skip("oracle/_ref/libqdldl_ref.so not built")
+    L = _capi.lib()
+    d = synth.make_systems(n, N, batch=1, seed=5, nan_pads=True)
+    S = torch.from_numpy(d["S"][0]).cuda()
+    nnz = L.gbd_schur_csr_nnz(n, N)
+    assert nnz == qdldl.nnz(n, N)
+    cp = torch.full((n * N + 1,), -1, dtype=torch.int32, device="cuda")
+    ri = torch.full((nnz,), -1, dtype=torch.int32, device="cuda")
+    val = torch.full((nnz,), float("nan"), device="cuda")
+    assert L.gbd_schur_csr_pattern_i32(n, N, cp.data_ptr(), ri.data_ptr(), 0) == 0
+    assert L.gbd_schur_csr_values_f32(n, N, S.data_ptr(), val.data_ptr(), 0) == 0
+    torch.cuda.synchronize()
+    wcp, wri = qdldl.pattern(n, N)
+    assert np.array_equal(cp.cpu().numpy(), wcp) and np.array_equal(ri.cpu().numpy(), wri)
+    wval = qdldl.values(d["S"][0], n, N)[0]
+    assert np.array_equal(val.cpu().numpy(), wval)
+    if n == 14:
+        # the reference's QDLDL on the GPU-packed matrix vs our PCG on the band form of the same system
+        import ctypes as C
+        ws = qdldl.lib().qdldl_ref_create(n, N)
+        x = np.zeros(n * N, np.float32)
+        v = np.ascontiguousarray(val.cpu().numpy())
+        g = np.ascontiguousarray(d["gamma"][0])
+        fp = C.POINTER(C.c_float)
+        assert qdldl.lib().qdldl_ref_solve(ws, v.ctypes.data_as(fp), g.ctypes.data_as(fp), x.ctypes.data_as(fp)) >= 0
+        qdldl.lib().qdldl_ref_destroy(ws)
+        P, gam = torch.from_numpy(d["Pinv"][0]).cuda(), torch.from_numpy(d["gamma"][0]).cuda()
+        lam = torch.zeros(n * N, device="cuda")
+        it = torch.zeros(1, dtype=torch.int32, device="cuda")
+        fl = torch.zeros(1, dtype=torch.uint8, device="cuda")
+        mp.pcg_launch(n, N, S, P, gam, lam, None, None, None, None, it, fl, 500, 1e-9)
+        torch.cuda.synchronize()
+        lam = lam.cpu().numpy()
+        assert np.abs(lam - x).max() <= 2e-3 * np.abs(x).max()
