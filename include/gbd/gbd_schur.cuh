@@ -45,19 +45,30 @@ __device__ __forceinline__ float fma_(float a, float b, float c) { return __fmaf
 // rowv[c]/piv); then one FMA per element.  Same operands and operations per element as the reference -> same bits,
 // with ~2x fewer instructions and half the dependent latency of the shared-memory-resident version.
 // A: in shared memory, V (DIM x DIM, column-major) followed by DIM x DIM floats that receive V^-1.  snap: 32 floats, 16-B aligned.
+// core: rows in registers in, rows of [.. | V^-1] in registers out (a[DIM .. 2 DIM) of lane r = row r of the inverse)
 template <uint32_t DIM, bool DIV>
-__device__ __forceinline__ void gj_warp(float *A, float *snap, uint32_t lane)
+__device__ __forceinline__ void gj_regs(float (&a)[2 * DIM], float *snap, uint32_t lane)
 {
     static_assert(DIM + 1 <= 16, "one warp: row factors in lanes 0..15, new pivot row in lanes 16..31");
-    float *row = snap, *nrow = snap + 16;
-    const uint32_t r = lane < DIM ? lane : 0;            // lanes DIM..15 and 16.. shadow row 0 (never stored)
-    const uint32_t cI = lane >= 16 ? (lane - 16 <= DIM ? lane - 16 : 0) : 0;
-    float a[2 * DIM];
+    if constexpr (!DIV) {
+        // single-matrix form: every quotient is a product with pvInv = 1 / piv, so no lane needs another lane's division:
+        // the pivot row travels by shuffles and every lane forms the new pivot row itself -- no shared-memory round trip
+        (void)snap;
 #pragma unroll
-    for (uint32_t c = 0; c < DIM; ++c) {
-        a[c] = A[c * DIM + r];
-        a[DIM + c] = (c == r) ? 1.0f : 0.0f;
+        for (uint32_t p = 0; p < DIM; ++p) {
+            const float piv = __shfl_sync(0xffffffffu, a[p], p);
+            const float pv_inv = __fdiv_rn(1.0f, piv);
+            const float f = __fmul_rn(a[p], pv_inv);
+#pragma unroll
+            for (uint32_t c = 0; c <= DIM; ++c) {
+                const float rv = __shfl_sync(0xffffffffu, a[p + c], p);
+                a[p + c] = (lane == p) ? __fmul_rn(rv, pv_inv) : fma_(-f, rv, a[p + c]);
+            }
+        }
+        return;
     }
+    float *row = snap, *nrow = snap + 16;
+    const uint32_t cI = lane >= 16 ? (lane - 16 <= DIM ? lane - 16 : 0) : 0;
 #pragma unroll
     for (uint32_t p = 0; p < DIM; ++p) {
         if (lane == p) {
@@ -67,13 +78,25 @@ __device__ __forceinline__ void gj_warp(float *A, float *snap, uint32_t lane)
         __syncwarp();
         const float piv = row[0];
         const float num = lane < 16 ? a[p] : row[cI];
-        const float q = DIV ? __fdiv_rn(num, piv) : __fmul_rn(num, __fdiv_rn(1.0f, piv));
+        const float q = __fdiv_rn(num, piv);
         if (lane >= 16 && lane - 16 <= DIM) nrow[cI] = q;
         __syncwarp();
 #pragma unroll
         for (uint32_t c = 0; c <= DIM; ++c) a[p + c] = (lane == p) ? nrow[c] : fma_(-q, row[c], a[p + c]);
         __syncwarp();
     }
+}
+template <uint32_t DIM, bool DIV>
+__device__ __forceinline__ void gj_warp(float *A, float *snap, uint32_t lane)
+{
+    const uint32_t r = lane < DIM ? lane : 0;            // lanes DIM..15 and 16.. shadow row 0 (never stored)
+    float a[2 * DIM];
+#pragma unroll
+    for (uint32_t c = 0; c < DIM; ++c) {
+        a[c] = A[c * DIM + r];
+        a[DIM + c] = (c == r) ? 1.0f : 0.0f;
+    }
+    gj_regs<DIM, DIV>(a, snap, lane);
     if (lane < DIM) {
 #pragma unroll
         for (uint32_t c = 0; c < DIM; ++c) A[(DIM + c) * DIM + lane] = a[DIM + c];

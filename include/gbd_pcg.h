@@ -166,6 +166,17 @@ uint32_t gbd_schur_csr_nnz(uint32_t n, uint32_t N);
 int gbd_schur_csr_pattern_i32(uint32_t n, uint32_t N, int32_t *d_col_ptr, int32_t *d_row_ind, void *stream);
 int gbd_schur_csr_values_f32(uint32_t n, uint32_t N, const float *d_S, float *d_val, void *stream);
 
+/*
+ * Direct solve of S lambda = gamma by block cyclic reduction (the GPU alternative to the reference's
+ * CPU QDLDL path, include/qdldl/sqp.cuh:22-49, for systems on which PCG runs into its cap).  Same band layout as
+ * gbd_pcg_solve_f32; no preconditioner, no initial guess, no iteration count.  A different algorithm from the reference's
+ * two solvers: results agree with them to fp32 solver tolerance, not bit for bit.  Asynchronous on `stream`.
+ */
+int gbd_bcr_supported(uint32_t n, uint32_t N);
+int gbd_bcr_solve_f32(uint32_t n, uint32_t N, const float *d_S, const float *d_gamma, float *d_lambda, void *stream);
+int gbd_bcr_solve_batched_f32(uint32_t n, uint32_t N, uint32_t batch, const float *d_S, const float *d_gamma, float *d_lambda,
+                              void *stream);
+
 /* Number of kernels this library has launched in this process (for bench.py's gpu_launches). */
 uint64_t gbd_pcg_launch_count(void);
 

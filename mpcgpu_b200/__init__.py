@@ -6,8 +6,8 @@ drop-in headers under ``include/``; this Python package is the thin host mirror 
 and the benchmark.  There is no CPU / PyTorch fallback: a missing library or GPU raises.
 """
 from .solver import (HostPlan, PcgConfig, compute_dz, form_schur_system, linsys_window, pcg_launch,  # noqa: F401
-                     StepPlan, solve_batched, solvePCG, solvePCG_device)
+                     StepPlan, solve_batched, solve_direct, solvePCG, solvePCG_device)
 from . import synth  # noqa: F401
 
-__all__ = ["HostPlan", "PcgConfig", "StepPlan", "compute_dz", "form_schur_system", "linsys_window", "pcg_launch", "solve_batched", "solvePCG",
+__all__ = ["HostPlan", "PcgConfig", "StepPlan", "solve_direct", "compute_dz", "form_schur_system", "linsys_window", "pcg_launch", "solve_batched", "solvePCG",
            "solvePCG_device", "synth"]

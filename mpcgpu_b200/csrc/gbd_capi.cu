@@ -16,6 +16,7 @@
 #include "../../include/gbd/gbd_cluster_pcg_v4.cuh"
 #include "../../include/gbd/gbd_cluster_pcg_v5.cuh"
 #include "../../include/gbd/gbd_schur.cuh"
+#include "../../include/gbd/gbd_bcr.cuh"
 #include <map>
 
 namespace {
@@ -721,6 +722,77 @@ int gbd_step_results(gbd_step_plan *p, uint32_t *h_iters, uint8_t *h_flags, void
 }
 
 const uint8_t *gbd_step_device_flags(gbd_step_plan *p) { return p ? p->d_flag : nullptr; }
+
+}  // extern "C"
+
+// ---- f4: direct solve by block cyclic reduction in one cluster (include/gbd/gbd_bcr.cuh)
+namespace {
+template <uint32_t n, uint32_t N, uint32_t C>
+int bcr_launch(uint32_t batch, const float *S, const float *g, float *lam, cudaStream_t st)
+{
+    using K = gbd::BcrShape<n, N, C>;
+    auto kern = gbd::bcr_cluster_kernel<n, N, C>;
+    static bool prepared = false;
+    static int max_clusters = 0;
+    if (!prepared) {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (!prepared) {
+            if (K::SMEM_BYTES > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES));
+            if (C > 8) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            cudaLaunchConfig_t q = {};
+            cudaLaunchAttribute qa[1];
+            q.gridDim = dim3(C * 1024); q.blockDim = dim3(K::NT); q.dynamicSmemBytes = K::SMEM_BYTES;
+            qa[0].id = cudaLaunchAttributeClusterDimension;
+            qa[0].val.clusterDim.x = C; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+            q.attrs = qa; q.numAttrs = 1;
+            CK(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &q));
+            if (max_clusters < 1) max_clusters = 1;
+            prepared = true;
+        }
+    }
+    gbd::BcrArgs a{S, g, lam, batch};
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[1];
+    cfg.gridDim = dim3(C * (batch < (uint32_t)max_clusters ? batch : (uint32_t)max_clusters));
+    cfg.blockDim = dim3(K::NT);
+    cfg.dynamicSmemBytes = K::SMEM_BYTES;
+    cfg.stream = st;
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&cfg, kern, a));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return GBD_PCG_OK;
+}
+}  // namespace
+
+// (state_size, knot_points, CTAs per system) compiled in for the direct solver
+#define GBD_BCR_SHAPES(X) X(14, 8, 1) X(14, 16, 2) X(14, 32, 4) X(14, 64, 8) X(14, 128, 16) X(14, 256, 16) X(14, 512, 16) X(6, 16, 2) X(2, 4, 1)
+
+extern "C" {
+
+int gbd_bcr_supported(uint32_t n, uint32_t N)
+{
+#define X(a, b, c) if (n == a && N == b) return 1;
+    GBD_BCR_SHAPES(X)
+#undef X
+    return 0;
+}
+
+int gbd_bcr_solve_batched_f32(uint32_t n, uint32_t N, uint32_t batch, const float *d_S, const float *d_gamma, float *d_lambda,
+                              void *stream)
+{
+    if (!d_S || !d_gamma || !d_lambda || batch == 0) return GBD_PCG_ERR_BADARG;
+#define X(a, b, c) if (n == a && N == b) return bcr_launch<a, b, c>(batch, d_S, d_gamma, d_lambda, (cudaStream_t)stream);
+    GBD_BCR_SHAPES(X)
+#undef X
+    return GBD_PCG_ERR_UNSUPPORTED;
+}
+
+int gbd_bcr_solve_f32(uint32_t n, uint32_t N, const float *d_S, const float *d_gamma, float *d_lambda, void *stream)
+{
+    return gbd_bcr_solve_batched_f32(n, N, 1, d_S, d_gamma, d_lambda, stream);
+}
 
 // ---- f4: the QDLDL wire format of the band matrix (include/utils/csr.cuh)
 uint32_t gbd_schur_csr_nnz(uint32_t n, uint32_t N) { return gbd::csr_nnz(n, N); }

@@ -256,3 +256,16 @@ class StepPlan:
             self.close()
         except Exception:
             pass
+
+
+def solve_direct(state_size, knot_points, d_S, d_gamma, d_lambda, batch: int = 1, stream=None):
+    """Direct solve of S lambda = gamma by block cyclic reduction (gbd_bcr_solve_batched_f32): the GPU alternative to the
+    reference's CPU QDLDL path (include/qdldl/sqp.cuh:22-49).  Same band layout as pcg_launch; no preconditioner, no initial
+    guess.  A different algorithm from the reference's solvers: agreement is to fp32 solver tolerance.  Asynchronous."""
+    import torch
+    n, N = state_size, knot_points
+    for name, t, cnt in (("d_S", d_S, 3 * n * n * N * batch), ("d_gamma", d_gamma, n * N * batch), ("d_lambda", d_lambda, n * N * batch)):
+        if not t.is_cuda or not t.is_contiguous() or t.dtype != torch.float32 or t.numel() != cnt:
+            raise ValueError(f"{name}: expected a contiguous CUDA float32 tensor of {cnt} elements")
+    _capi.check(_capi.lib().gbd_bcr_solve_batched_f32(n, N, batch, _ptr(d_S), _ptr(d_gamma), _ptr(d_lambda), _stream(stream)),
+                "gbd_bcr_solve_batched_f32")
