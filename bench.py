@@ -578,6 +578,31 @@ def run_ours(args):
                 "form_schur_us": t_fs, "compute_dz_us": t_dzz, "launches_per_call": {"form_schur": 2, "compute_dz": 1}}
         except Exception as e:                                 # the extras never fail the bench line
             extras["sqp_neighbours"] = {"error": repr(e)[:200]}
+    # ---------------- row f4: the direct solver (block cyclic reduction) on the same ring of systems and on a 1024 batch
+    if rank == 0 and not args.no_configs:
+        try:
+            dlam = torch.zeros(n * N, device=dev)
+
+            def dsolve(q):
+                i = q % ring
+                rc = L.gbd_bcr_solve_f32(n, N, dS[i].data_ptr(), dg[i].data_ptr(), dlam.data_ptr(), stream)
+                assert rc == 0, rc
+
+            for q in range(20):
+                dsolve(q)
+            torch.cuda.synchronize()
+            d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            d0.record()
+            for q in range(400):
+                dsolve(q)
+            d1.record()
+            torch.cuda.synchronize()
+            extras["direct_solver"] = {
+                "what": "gbd_bcr_solve_f32: block cyclic reduction in one 16-CTA cluster, no preconditioner, no iteration cap "
+                        "(GPU alternative to the reference's CPU QDLDL path; accuracy and A/B in profiles/r01c_ab_direct.json)",
+                "kernel_us": 1e3 * d0.elapsed_time(d1) / 400, "solves_per_sec": 400 / (d0.elapsed_time(d1) * 1e-3)}
+        except Exception as e:
+            extras["direct_solver"] = {"error": repr(e)[:200]}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline({k: (host[k][:64] if isinstance(host[k], np.ndarray) else host[k]) for k in host},

@@ -59,10 +59,11 @@ struct BcrArgs {
     const float *gamma;   // [batch][N*n]
     float *lambda;        // [batch][N*n]  out
     uint32_t batch;
+    uint32_t *dbg;        // timeline build only: %clock stamps [stamp][CTA][warp] (gbd_pcg_set_debug_buffer, tools/timeline_bcr.py)
 };
 
-template <uint32_t n, uint32_t N, uint32_t C>
-__global__ void __launch_bounds__(BcrShape<n, N, C>::NT, 1)
+template <uint32_t n, uint32_t N, uint32_t C, uint32_t MINB, bool PROF = false>
+__global__ void __launch_bounds__(BcrShape<n, N, C>::NT, MINB)
 bcr_cluster_kernel(const BcrArgs a)
 {
     using K = BcrShape<n, N, C>;
@@ -77,14 +78,39 @@ bcr_cluster_kernel(const BcrArgs a)
     const bool act = lane < n;
     const uint32_t rows_u = smem_u32(rows);
 
+    uint32_t nstamp = 0;
+    auto stamp = [&]() {                                 // timeline build: one %clock per warp per call site, in program order
+        if constexpr (PROF) {
+            if (a.dbg && lane == 0) {
+                uint32_t c_;
+                asm volatile("mov.u32 %0, %%clock;" : "=r"(c_)::"memory");
+                a.dbg[(nstamp * C + cr) * K::WARPS + warp] = c_;
+            }
+            ++nstamp;
+        }
+    };
     auto rec = [&](uint32_t grow) -> float * { return rows + (size_t)(grow - cr * R) * ROWF; };          // local rows only
     auto rec_cluster = [&](uint32_t grow, uint32_t off) -> uint32_t {                                     // any row of the system
         return map_to_cta(rows_u + 4u * ((grow % R) * ROWF + off), grow / R);
     };
     // copy W of row j (any CTA) into a per-warp buffer: 128-bit DSMEM loads, all lanes
     auto fetch_w = [&](uint32_t j, float *dst) {
-        const uint32_t src = rec_cluster(j, K::OFF_W);
-        for (uint32_t q = lane; q < WF / 4; q += 32) reinterpret_cast<float4 *>(dst)[q] = ld_cluster_f4(src + 16u * q);
+        constexpr uint32_t Q = (WF / 4 + 31) / 32;          // all of a lane's loads are issued before the first store
+        float4 v[Q];
+        if (j / R == cr) {                                   // neighbour in this CTA: plain shared-memory loads
+            const float4 *src = reinterpret_cast<const float4 *>(rec(j) + K::OFF_W);
+#pragma unroll
+            for (uint32_t q = 0; q < Q; ++q)
+                if (lane + 32 * q < WF / 4) v[q] = src[lane + 32 * q];
+        } else {
+            const uint32_t src = rec_cluster(j, K::OFF_W);
+#pragma unroll
+            for (uint32_t q = 0; q < Q; ++q)
+                if (lane + 32 * q < WF / 4) v[q] = ld_cluster_f4(src + 16u * (lane + 32 * q));
+        }
+#pragma unroll
+        for (uint32_t q = 0; q < Q; ++q)
+            if (lane + 32 * q < WF / 4) reinterpret_cast<float4 *>(dst)[lane + 32 * q] = v[q];
     };
     // tasks of this warp at stride s: rows first, first + 2s, ... inside this CTA (or the single row cr*R when 2s > R)
     auto for_rows = [&](uint32_t s, uint32_t residue, auto &&body) {
@@ -108,6 +134,7 @@ bcr_cluster_kernel(const BcrArgs a)
         }
         for (uint32_t i = t; i < R * n; i += NT) rows[(size_t)(i / n) * ROWF + K::OFF_B + i % n] = gb[i];
         __syncthreads();
+        stamp();
 
         // ---- forward reduction
         for (uint32_t s = 1; s < N; s <<= 1) {
@@ -120,7 +147,7 @@ bcr_cluster_kernel(const BcrArgs a)
                     m[c] = rj[K::OFF_D + r + c * n];
                     m[n + c] = (c == r) ? 1.0f : 0.0f;
                 }
-                schur_detail::gj_regs<n, false>(m, snap, lane);
+                schur_detail::gj_regs<n, false, true>(m, snap, lane);
                 // W = D^-1 [L | U | b]: lane r forms row r; [L | U | b] is contiguous in the record.  k outermost: the WC
                 // accumulators of a lane are independent chains (ILP), operands come in as 64-bit broadcast loads
                 const float *X = rj + K::OFF_L;
@@ -146,7 +173,9 @@ bcr_cluster_kernel(const BcrArgs a)
                         if (act && c0 + c < WC) rj[K::OFF_W + r + (c0 + c) * n] = acc[c];
                 }
             });
+            stamp();
             cluster_sync();                                // W of every eliminated row visible cluster-wide
+            stamp();
             // phase 2: rows i = 0 (mod 2s) absorb their eliminated neighbours
             for_rows(s, 0, [&](uint32_t i) {
                 float *ri = rec(i);
@@ -206,7 +235,9 @@ bcr_cluster_kernel(const BcrArgs a)
                 if (act) ri[K::OFF_B + r] -= bl + bu;
                 __syncwarp();
             });
+            stamp();
             __syncthreads();                               // the updated rows are read next by warps of this CTA only
+            stamp();
         }
         // ---- root: x_0 = D_0^-1 b_0 (row 0 lives in CTA 0)
         if (cr == 0 && warp == 0) {
@@ -217,13 +248,15 @@ bcr_cluster_kernel(const BcrArgs a)
                 m[c] = r0[K::OFF_D + r + c * n];
                 m[n + c] = (c == r) ? 1.0f : 0.0f;
             }
-            schur_detail::gj_regs<n, false>(m, snap, lane);
+            schur_detail::gj_regs<n, false, true>(m, snap, lane);
             float acc = 0.0f;
 #pragma unroll
             for (uint32_t k = 0; k < n; ++k) acc = fma_rn(m[n + k], r0[K::OFF_B + k], acc);
             if (act) r0[K::OFF_X + r] = acc;
         }
+        stamp();
         cluster_sync();
+        stamp();
         // ---- back substitution, strides descending
         for (uint32_t s = N / 2; s >= 1; s >>= 1) {
             for_rows(s, s % (2 * s), [&](uint32_t j) {
@@ -242,6 +275,7 @@ bcr_cluster_kernel(const BcrArgs a)
         }
         // ---- output
         float *gl = a.lambda + (size_t)sys * N * n + (size_t)cr * R * n;
+        stamp();
         for (uint32_t i = t; i < R * n; i += NT) gl[i] = rows[(size_t)(i / n) * ROWF + K::OFF_X + i % n];
         cluster_sync();                                    // nobody reloads rows while a peer may still read x / W
     }

@@ -46,10 +46,13 @@ __device__ __forceinline__ float fma_(float a, float b, float c) { return __fmaf
 // with ~2x fewer instructions and half the dependent latency of the shared-memory-resident version.
 // A: in shared memory, V (DIM x DIM, column-major) followed by DIM x DIM floats that receive V^-1.  snap: 32 floats, 16-B aligned.
 // core: rows in registers in, rows of [.. | V^-1] in registers out (a[DIM .. 2 DIM) of lane r = row r of the inverse)
-template <uint32_t DIM, bool DIV>
+// FAST_RCP (direct solver only, never on a bit-exact path): pvInv from the hardware reciprocal (1 ulp) instead of an IEEE
+// division -- the reciprocal sits on the 14-step dependent pivot chain.
+template <uint32_t DIM, bool DIV, bool FAST_RCP = false>
 __device__ __forceinline__ void gj_regs(float (&a)[2 * DIM], float *snap, uint32_t lane)
 {
     static_assert(DIM + 1 <= 16, "one warp: row factors in lanes 0..15, new pivot row in lanes 16..31");
+    static_assert(!FAST_RCP || !DIV, "the fast reciprocal only exists for the single-matrix form");
     if constexpr (!DIV) {
         // single-matrix form: every quotient is a product with pvInv = 1 / piv, so no lane needs another lane's division:
         // the pivot row travels by shuffles and every lane forms the new pivot row itself -- no shared-memory round trip
@@ -57,7 +60,9 @@ __device__ __forceinline__ void gj_regs(float (&a)[2 * DIM], float *snap, uint32
 #pragma unroll
         for (uint32_t p = 0; p < DIM; ++p) {
             const float piv = __shfl_sync(0xffffffffu, a[p], p);
-            const float pv_inv = __fdiv_rn(1.0f, piv);
+            float pv_inv;
+            if constexpr (FAST_RCP) asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(pv_inv) : "f"(piv));
+            else pv_inv = __fdiv_rn(1.0f, piv);
             const float f = __fmul_rn(a[p], pv_inv);
 #pragma unroll
             for (uint32_t c = 0; c <= DIM; ++c) {

@@ -727,11 +727,13 @@ const uint8_t *gbd_step_device_flags(gbd_step_plan *p) { return p ? p->d_flag : 
 
 // ---- f4: direct solve by block cyclic reduction in one cluster (include/gbd/gbd_bcr.cuh)
 namespace {
-template <uint32_t n, uint32_t N, uint32_t C>
+// MINB = 1: all registers to one CTA per SM (lowest latency, single solves); MINB = 4: 128-register build so that four
+// CTAs share an SM (more systems in flight, batches)
+template <uint32_t n, uint32_t N, uint32_t C, uint32_t MINB, bool PROF = false>
 int bcr_launch(uint32_t batch, const float *S, const float *g, float *lam, cudaStream_t st)
 {
     using K = gbd::BcrShape<n, N, C>;
-    auto kern = gbd::bcr_cluster_kernel<n, N, C>;
+    auto kern = gbd::bcr_cluster_kernel<n, N, C, MINB, PROF>;
     static bool prepared = false;
     static int max_clusters = 0;
     if (!prepared) {
@@ -750,7 +752,7 @@ int bcr_launch(uint32_t batch, const float *S, const float *g, float *lam, cudaS
             prepared = true;
         }
     }
-    gbd::BcrArgs a{S, g, lam, batch};
+    gbd::BcrArgs a{S, g, lam, batch, PROF ? g_dbg : nullptr};
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute at[1];
     cfg.gridDim = dim3(C * (batch < (uint32_t)max_clusters ? batch : (uint32_t)max_clusters));
@@ -783,7 +785,8 @@ int gbd_bcr_solve_batched_f32(uint32_t n, uint32_t N, uint32_t batch, const floa
                               void *stream)
 {
     if (!d_S || !d_gamma || !d_lambda || batch == 0) return GBD_PCG_ERR_BADARG;
-#define X(a, b, c) if (n == a && N == b) return bcr_launch<a, b, c>(batch, d_S, d_gamma, d_lambda, (cudaStream_t)stream);
+#define X(a, b, c) if (n == a && N == b) return batch > 1 ? bcr_launch<a, b, c, 4>(batch, d_S, d_gamma, d_lambda, (cudaStream_t)stream) \
+                                                        : bcr_launch<a, b, c, 1>(batch, d_S, d_gamma, d_lambda, (cudaStream_t)stream);
     GBD_BCR_SHAPES(X)
 #undef X
     return GBD_PCG_ERR_UNSUPPORTED;
@@ -791,6 +794,9 @@ int gbd_bcr_solve_batched_f32(uint32_t n, uint32_t N, uint32_t batch, const floa
 
 int gbd_bcr_solve_f32(uint32_t n, uint32_t N, const float *d_S, const float *d_gamma, float *d_lambda, void *stream)
 {
+    // timeline build (diagnostics): with a debug buffer set, the IIWA N = 128 / 32 shapes run the stamped kernel
+    if (g_dbg && n == 14 && N == 128) return bcr_launch<14, 128, 16, 1, true>(1, d_S, d_gamma, d_lambda, (cudaStream_t)stream);
+    if (g_dbg && n == 14 && N == 32) return bcr_launch<14, 32, 4, 1, true>(1, d_S, d_gamma, d_lambda, (cudaStream_t)stream);
     return gbd_bcr_solve_batched_f32(n, N, 1, d_S, d_gamma, d_lambda, stream);
 }
 
