@@ -17,6 +17,7 @@
 // into a per-warp buffer with 128-bit loads); one cluster barrier between phase 1 and phase 2 and per back-substitution level.
 // Dependent chain: log2(N) x (14-pivot inversion + two n x n x (2n+1) products) -- about 20 us at n = 14, N = 128.
 #pragma once
+#include <type_traits>
 #include "gbd_device.cuh"
 #include "gbd_schur.cuh"
 
@@ -153,25 +154,28 @@ bcr_cluster_kernel(const BcrArgs a)
                 const float *X = rj + K::OFF_L;
                 static_assert(n % 2 == 0, "64-bit operand loads");
                 constexpr uint32_t CH = (WC + 1) / 2;              // two passes over the columns keep the accumulators in registers
-#pragma unroll 1
-                for (uint32_t c0 = 0; c0 < WC; c0 += CH) {
-                    float acc[CH];
+                auto w_pass = [&](auto c0_tag) {                   // compile-time column base: no index arithmetic in the loop
+                    constexpr uint32_t c0 = decltype(c0_tag)::value;
+                    constexpr uint32_t CNT = c0 + CH <= WC ? CH : WC - c0;
+                    float acc[CNT];
 #pragma unroll
-                    for (uint32_t c = 0; c < CH; ++c) acc[c] = 0.0f;
+                    for (uint32_t c = 0; c < CNT; ++c) acc[c] = 0.0f;
 #pragma unroll
                     for (uint32_t k = 0; k < n; k += 2) {
 #pragma unroll
-                        for (uint32_t c = 0; c < CH; ++c) {
-                            const uint32_t cc = c0 + c < WC ? c0 + c : WC - 1;
-                            const float2 x2 = *reinterpret_cast<const float2 *>(X + k + cc * n);
+                        for (uint32_t c = 0; c < CNT; ++c) {
+                            const float2 x2 = *reinterpret_cast<const float2 *>(X + k + (c0 + c) * n);
                             acc[c] = fma_rn(m[n + k], x2.x, acc[c]);
                             acc[c] = fma_rn(m[n + k + 1], x2.y, acc[c]);
                         }
                     }
+                    if (act) {
 #pragma unroll
-                    for (uint32_t c = 0; c < CH; ++c)
-                        if (act && c0 + c < WC) rj[K::OFF_W + r + (c0 + c) * n] = acc[c];
-                }
+                        for (uint32_t c = 0; c < CNT; ++c) rj[K::OFF_W + r + (c0 + c) * n] = acc[c];
+                    }
+                };
+                w_pass(std::integral_constant<uint32_t, 0>{});
+                w_pass(std::integral_constant<uint32_t, CH>{});
             });
             stamp();
             cluster_sync();                                // W of every eliminated row visible cluster-wide
@@ -186,13 +190,14 @@ bcr_cluster_kernel(const BcrArgs a)
                 // one neighbour at a time (register budget): lane r holds row r of the coupling block, 2 n + 1 accumulators in
                 // flight, k outermost, 64-bit broadcast loads of the neighbour's W copy
                 float bl = 0.0f, bu = 0.0f;
-                auto absorb = [&](const float *w, uint32_t off_c, bool minus_side, float &bacc) {
+                auto absorb = [&](const float *w, uint32_t off_c, auto side_tag, float &bacc) {
+                    constexpr bool minus_side = decltype(side_tag)::value;
                     float crow[n];
 #pragma unroll
                     for (uint32_t k = 0; k < n; ++k) crow[k] = ri[off_c + r + k * n];
                     constexpr uint32_t CH = n / 2;                 // two passes over the columns keep the accumulators in registers
-#pragma unroll 1
-                    for (uint32_t c0 = 0; c0 < n; c0 += CH) {
+                    auto a_pass = [&](auto c0_tag) {
+                        constexpr uint32_t c0 = decltype(c0_tag)::value;
                         float dacc[CH], nacc[CH];
 #pragma unroll
                         for (uint32_t c = 0; c < CH; ++c) { dacc[c] = 0.0f; nacc[c] = 0.0f; }
@@ -215,19 +220,21 @@ bcr_cluster_kernel(const BcrArgs a)
                                 ri[off_c + r + (c0 + c) * n] = -nacc[c];
                             }
                         }
-                    }
+                    };
+                    a_pass(std::integral_constant<uint32_t, 0>{});
+                    a_pass(std::integral_constant<uint32_t, CH>{});
 #pragma unroll
                     for (uint32_t k = 0; k < n; k += 2) {
                         const float2 wb = *reinterpret_cast<const float2 *>(w + k + 2 * n * n);
                         bacc = fma_rn(crow[k], wb.x, bacc); bacc = fma_rn(crow[k + 1], wb.y, bacc);
                     }
                 };
-                if (has_m) absorb(wm, K::OFF_L, true, bl);
+                if (has_m) absorb(wm, K::OFF_L, std::true_type{}, bl);
                 else if (act) {
 #pragma unroll
                     for (uint32_t c = 0; c < n; ++c) ri[K::OFF_L + r + c * n] = 0.0f;
                 }
-                if (has_p) absorb(wp, K::OFF_U, false, bu);
+                if (has_p) absorb(wp, K::OFF_U, std::false_type{}, bu);
                 else if (act) {
 #pragma unroll
                     for (uint32_t c = 0; c < n; ++c) ri[K::OFF_U + r + c * n] = 0.0f;
@@ -271,7 +278,8 @@ bcr_cluster_kernel(const BcrArgs a)
                 }
                 if (act) rj[K::OFF_X + r] = acc;
             });
-            cluster_sync();
+            // rows at distance < R from their neighbours only read x of this CTA or of rows solved before the last cluster barrier
+            if (s >= R) cluster_sync(); else __syncthreads();
         }
         // ---- output
         float *gl = a.lambda + (size_t)sys * N * n + (size_t)cr * R * n;
