@@ -60,6 +60,7 @@ struct BcrArgs {
     const float *gamma;   // [batch][N*n]
     float *lambda;        // [batch][N*n]  out
     uint32_t batch;
+    const uint8_t *only_if;   // nullable [batch]: solve system i only where only_if[i] != 0 (PCG's max_iter_exit flags)
     uint32_t *dbg;        // timeline build only: %clock stamps [stamp][CTA][warp] (gbd_pcg_set_debug_buffer, tools/timeline_bcr.py)
 };
 
@@ -123,6 +124,7 @@ bcr_cluster_kernel(const BcrArgs a)
     };
 
     for (uint32_t sys = cluster_idx(); sys < a.batch; sys += cluster_count()) {
+        if (a.only_if && a.only_if[sys] == 0) continue;   // cluster-uniform: every CTA reads the same byte
         const float *gS = a.S + ((size_t)sys * N + (size_t)cr * R) * 3 * nn;
         const float *gb = a.gamma + (size_t)sys * N * n + (size_t)cr * R * n;
         // ---- load: tiles [left | diag | right] -> L, D, U ; the two tiles the format never defines are zero

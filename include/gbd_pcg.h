@@ -153,6 +153,10 @@ int gbd_step_plan_create(uint32_t n, uint32_t m, uint32_t N, uint32_t batch, gbd
 int gbd_step_plan_destroy(gbd_step_plan *plan);
 int gbd_step_run_f32(gbd_step_plan *plan, float *d_G, const float *d_C, const float *d_g, const float *d_c, float rho,
                      float *d_lambda, float *d_dz, uint32_t max_iter, float exit_tol, void *stream);
+/* gbd_step_run_f32 with a direct fallback: trajectories whose PCG solve hit max_iter are re-solved by gbd_bcr_solve_flagged_f32
+ * before dz is formed (their max_iter_exit flags stay set, so the caller still sees which ones they were). */
+int gbd_step_run_fallback_f32(gbd_step_plan *plan, float *d_G, const float *d_C, const float *d_g, const float *d_c, float rho,
+                              float *d_lambda, float *d_dz, uint32_t max_iter, float exit_tol, void *stream);
 int gbd_step_results(gbd_step_plan *plan, uint32_t *h_iters, uint8_t *h_max_iter_exit, void *stream);
 const uint8_t *gbd_step_device_flags(gbd_step_plan *plan);
 
@@ -176,6 +180,10 @@ int gbd_bcr_supported(uint32_t n, uint32_t N);
 int gbd_bcr_solve_f32(uint32_t n, uint32_t N, const float *d_S, const float *d_gamma, float *d_lambda, void *stream);
 int gbd_bcr_solve_batched_f32(uint32_t n, uint32_t N, uint32_t batch, const float *d_S, const float *d_gamma, float *d_lambda,
                               void *stream);
+/* Same, but only for the systems i with d_only_if[i] != 0 -- e.g. the max_iter_exit flags of a batched PCG solve: the
+ * trajectories on which PCG ran into its cap get the direct solution, the others keep their PCG solution. */
+int gbd_bcr_solve_flagged_f32(uint32_t n, uint32_t N, uint32_t batch, const float *d_S, const float *d_gamma, float *d_lambda,
+                              const uint8_t *d_only_if, void *stream);
 
 /* Number of kernels this library has launched in this process (for bench.py's gpu_launches). */
 uint64_t gbd_pcg_launch_count(void);

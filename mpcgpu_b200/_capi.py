@@ -19,7 +19,8 @@ SYMBOLS = [
     "gbd_pcg_launch_count", "gbd_pcg_set_debug_buffer", "gbd_schur_supported", "gbd_form_schur_system_f32",
     "gbd_compute_dz_f32", "gbd_step_plan_create", "gbd_step_plan_destroy", "gbd_step_run_f32", "gbd_step_results",
     "gbd_step_device_flags", "gbd_schur_csr_nnz", "gbd_schur_csr_pattern_i32", "gbd_schur_csr_values_f32",
-    "gbd_bcr_supported", "gbd_bcr_solve_f32", "gbd_bcr_solve_batched_f32",
+    "gbd_bcr_supported", "gbd_bcr_solve_f32", "gbd_bcr_solve_batched_f32", "gbd_bcr_solve_flagged_f32",
+    "gbd_step_run_fallback_f32",
 ]
 
 _lib = None
@@ -101,6 +102,10 @@ def lib():
     L.gbd_bcr_solve_f32.argtypes = [u32, u32, vp, vp, vp, vp]
     L.gbd_bcr_solve_batched_f32.restype = C.c_int
     L.gbd_bcr_solve_batched_f32.argtypes = [u32, u32, u32, vp, vp, vp, vp]
+    L.gbd_bcr_solve_flagged_f32.restype = C.c_int
+    L.gbd_bcr_solve_flagged_f32.argtypes = [u32, u32, u32, vp, vp, vp, vp, vp]
+    L.gbd_step_run_fallback_f32.restype = C.c_int
+    L.gbd_step_run_fallback_f32.argtypes = [vp, vp, vp, vp, vp, f32, vp, vp, u32, f32, vp]
     L.gbd_pcg_set_debug_buffer.restype = None
     L.gbd_pcg_set_debug_buffer.argtypes = [vp]
     _lib = L

@@ -689,8 +689,23 @@ int gbd_step_plan_destroy(gbd_step_plan *p)
     return GBD_PCG_OK;
 }
 
+static int step_run(gbd_step_plan *p, float *d_G, const float *d_C, const float *d_g, const float *d_c, float rho,
+                    float *d_lambda, float *d_dz, uint32_t max_iter, float exit_tol, void *stream, bool direct_fallback);
+
 int gbd_step_run_f32(gbd_step_plan *p, float *d_G, const float *d_C, const float *d_g, const float *d_c, float rho,
                      float *d_lambda, float *d_dz, uint32_t max_iter, float exit_tol, void *stream)
+{
+    return step_run(p, d_G, d_C, d_g, d_c, rho, d_lambda, d_dz, max_iter, exit_tol, stream, false);
+}
+
+int gbd_step_run_fallback_f32(gbd_step_plan *p, float *d_G, const float *d_C, const float *d_g, const float *d_c, float rho,
+                              float *d_lambda, float *d_dz, uint32_t max_iter, float exit_tol, void *stream)
+{
+    return step_run(p, d_G, d_C, d_g, d_c, rho, d_lambda, d_dz, max_iter, exit_tol, stream, true);
+}
+
+static int step_run(gbd_step_plan *p, float *d_G, const float *d_C, const float *d_g, const float *d_c, float rho,
+                    float *d_lambda, float *d_dz, uint32_t max_iter, float exit_tol, void *stream, bool direct_fallback)
 {
     if (!p || !d_G || !d_C || !d_g || !d_c || !d_lambda || !d_dz) return GBD_PCG_ERR_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
@@ -702,6 +717,10 @@ int gbd_step_run_f32(gbd_step_plan *p, float *d_G, const float *d_C, const float
     rc = launch<float>(p->n, p->N, p->batch, p->dS, p->dP, p->dgam, d_lambda, (float *)nullptr, (float *)nullptr, p->d_iters, p->d_flag,
                        max_iter, exit_tol, st);
     if (rc) return rc;
+    if (direct_fallback) {      // trajectories on which PCG ran into its cap are solved again, directly (their flags stay set)
+        rc = gbd_bcr_solve_flagged_f32(p->n, p->N, p->batch, p->dS, p->dgam, d_lambda, p->d_flag, stream);
+        if (rc) return rc;
+    }
     rc = GBD_PCG_ERR_UNSUPPORTED;
 #define X(a, b) if (p->n == a && p->m == b) rc = dz_launch<a, b>(p->N, p->batch, d_G, d_C, d_g, d_lambda, d_dz, st);
     GBD_SCHUR_SHAPES(X)
@@ -730,7 +749,7 @@ namespace {
 // MINB = 1: all registers to one CTA per SM (lowest latency, single solves); MINB = 4: 128-register build so that four
 // CTAs share an SM (more systems in flight, batches)
 template <uint32_t n, uint32_t N, uint32_t C, uint32_t MINB, bool PROF = false>
-int bcr_launch(uint32_t batch, const float *S, const float *g, float *lam, cudaStream_t st)
+int bcr_launch(uint32_t batch, const float *S, const float *g, float *lam, cudaStream_t st, const uint8_t *only_if = nullptr)
 {
     using K = gbd::BcrShape<n, N, C>;
     auto kern = gbd::bcr_cluster_kernel<n, N, C, MINB, PROF>;
@@ -752,7 +771,7 @@ int bcr_launch(uint32_t batch, const float *S, const float *g, float *lam, cudaS
             prepared = true;
         }
     }
-    gbd::BcrArgs a{S, g, lam, batch, PROF ? g_dbg : nullptr};
+    gbd::BcrArgs a{S, g, lam, batch, only_if, PROF ? g_dbg : nullptr};
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute at[1];
     cfg.gridDim = dim3(C * (batch < (uint32_t)max_clusters ? batch : (uint32_t)max_clusters));
@@ -787,6 +806,16 @@ int gbd_bcr_solve_batched_f32(uint32_t n, uint32_t N, uint32_t batch, const floa
     if (!d_S || !d_gamma || !d_lambda || batch == 0) return GBD_PCG_ERR_BADARG;
 #define X(a, b, c) if (n == a && N == b) return batch > 1 ? bcr_launch<a, b, c, 4>(batch, d_S, d_gamma, d_lambda, (cudaStream_t)stream) \
                                                         : bcr_launch<a, b, c, 1>(batch, d_S, d_gamma, d_lambda, (cudaStream_t)stream);
+    GBD_BCR_SHAPES(X)
+#undef X
+    return GBD_PCG_ERR_UNSUPPORTED;
+}
+
+int gbd_bcr_solve_flagged_f32(uint32_t n, uint32_t N, uint32_t batch, const float *d_S, const float *d_gamma, float *d_lambda,
+                              const uint8_t *d_only_if, void *stream)
+{
+    if (!d_S || !d_gamma || !d_lambda || !d_only_if || batch == 0) return GBD_PCG_ERR_BADARG;
+#define X(a, b, c) if (n == a && N == b) return bcr_launch<a, b, c, 4>(batch, d_S, d_gamma, d_lambda, (cudaStream_t)stream, d_only_if);
     GBD_BCR_SHAPES(X)
 #undef X
     return GBD_PCG_ERR_UNSUPPORTED;

@@ -218,16 +218,18 @@ class StepPlan:
         return dict(G=B * ((n * n + m * m) * (N - 1) + n * n), C=B * (n * n + n * m) * (N - 1), g=B * ((n + m) * (N - 1) + n),
                     c=B * n * N, lam=B * n * N, dz=B * ((n + m) * (N - 1) + n))
 
-    def run(self, d_G, d_C, d_g, d_c, rho, d_lambda, d_dz, max_iter, exit_tol, stream=None):
-        """Asynchronous.  d_G is overwritten with the block inverses; d_lambda is in/out; d_dz is written."""
+    def run(self, d_G, d_C, d_g, d_c, rho, d_lambda, d_dz, max_iter, exit_tol, stream=None, direct_fallback=False):
+        """Asynchronous.  d_G is overwritten with the block inverses; d_lambda is in/out; d_dz is written.
+        direct_fallback: trajectories whose PCG solve hits max_iter are re-solved directly (block cyclic reduction)."""
         import torch
         sz = self.sizes()
         for name, t, key in (("d_G", d_G, "G"), ("d_C", d_C, "C"), ("d_g", d_g, "g"), ("d_c", d_c, "c"), ("d_lambda", d_lambda, "lam"),
                              ("d_dz", d_dz, "dz")):
             if not t.is_cuda or not t.is_contiguous() or t.dtype != torch.float32 or t.numel() != sz[key]:
                 raise ValueError(f"{name}: expected a contiguous CUDA float32 tensor of {sz[key]} elements")
-        _capi.check(_capi.lib().gbd_step_run_f32(self._h, _ptr(d_G), _ptr(d_C), _ptr(d_g), _ptr(d_c), float(rho), _ptr(d_lambda),
-                                                 _ptr(d_dz), int(max_iter), float(exit_tol), _stream(stream)), "gbd_step_run_f32")
+        fn = _capi.lib().gbd_step_run_fallback_f32 if direct_fallback else _capi.lib().gbd_step_run_f32
+        _capi.check(fn(self._h, _ptr(d_G), _ptr(d_C), _ptr(d_g), _ptr(d_c), float(rho), _ptr(d_lambda), _ptr(d_dz), int(max_iter),
+                       float(exit_tol), _stream(stream)), "gbd_step_run_f32")
 
     def results(self, stream=None):
         """Blocks on the stream; returns (iters[batch] uint32, max_iter_exit[batch] uint8) of the last run."""

@@ -91,3 +91,35 @@ def test_direct_argument_errors(torch_cuda):
     assert L.gbd_bcr_supported(14, 128) == 1 and L.gbd_bcr_supported(14, 48) == 0
     assert L.gbd_bcr_solve_f32(14, 48, 1, 1, 1, 0) == _capi.ERR_UNSUPPORTED
     assert L.gbd_bcr_solve_f32(14, 128, 0, 1, 1, 0) == _capi.ERR_BADARG
+
+
+def test_step_with_direct_fallback(torch_cuda, oracle_pcg):
+    """gbd_step_run_fallback_f32: trajectories whose PCG solve hits the cap get the direct solution (fp64 residual small), the
+    converged ones keep their PCG solution bit for bit; dz is formed from whichever lambda was kept."""
+    torch = torch_cuda
+    import mpcgpu_b200 as mp
+    from oracle import schur
+    n, m, N, B = 14, 7, 32, 6
+    kk = [schur.make_kkt(n, m, N, seed=500 + i) for i in range(B)]
+    G, C, g, c = (np.concatenate([k[j] for k in kk]) for j in range(4))
+    out = {}
+    for fb in (False, True):
+        dG, dC, dg, dc = (torch.from_numpy(x.copy()).cuda() for x in (G, C, g, c))
+        dl = torch.zeros(B * n * N, device="cuda")
+        dz = torch.zeros(B * ((n + m) * (N - 1) + n), device="cuda")
+        plan = mp.StepPlan(n, m, N, B)
+        plan.run(dG, dC, dg, dc, 1e-3, dl, dz, 12, 1e-7, direct_fallback=fb)      # cap of 12: most trajectories hit it
+        it, fl = plan.results()
+        out[fb] = (dl.cpu().numpy().reshape(B, -1), dz.cpu().numpy().reshape(B, -1), fl.copy())
+        plan.close()
+    assert np.array_equal(out[False][2], out[True][2]) and out[True][2].any()
+    nz = (n + m) * (N - 1) + n
+    for i in range(B):
+        o = schur.form(kk[i][0], kk[i][1], kk[i][2], kk[i][3], n, m, N, 1e-3, pad=0.0)
+        if out[True][2][i]:
+            res_fb = oracle_pcg.rel_residual(o["S"], o["gamma"], out[True][0][i], n, N)
+            res_pcg = oracle_pcg.rel_residual(o["S"], o["gamma"], out[False][0][i], n, N)
+            assert res_fb < 5e-5 and res_fb < res_pcg, (i, res_fb, res_pcg)
+            assert np.array_equal(out[True][1][i], schur.dz(o["Ginv"], kk[i][1], kk[i][2], out[True][0][i], n, m, N))
+        else:
+            assert np.array_equal(out[True][0][i], out[False][0][i]) and np.array_equal(out[True][1][i], out[False][1][i])
