@@ -141,6 +141,63 @@ bcr_cluster_kernel(const BcrArgs a)
 
         // ---- forward reduction
         for (uint32_t s = 1; s < N; s <<= 1) {
+            // From the level on where a CTA holds at most one active row (2s >= R) its four warps share that row's work:
+            // warp 0 inverts, then each warp forms a quarter of the columns of W; in phase 2 each warp takes one side
+            // (i-s / i+s) and one half of the columns.  Below that level there is one warp per row (path further down).
+            const bool coop = 2 * s >= R;
+            if (coop) {
+                const bool has1 = (2 * s == R) || ((cr * R) % (2 * s) == s);
+                const uint32_t j = (2 * s == R) ? cr * R + s : cr * R;
+                float *rj = rec(has1 ? j : cr * R);
+                float *invbuf = bsm + (size_t)R * ROWF + WF;          // warp 0's second scratch buffer, read by all four warps
+                if (has1 && warp == 0) {
+                    float m[2 * n];
+#pragma unroll
+                    for (uint32_t c = 0; c < n; ++c) {
+                        m[c] = rj[K::OFF_D + r + c * n];
+                        m[n + c] = (c == r) ? 1.0f : 0.0f;
+                    }
+                    schur_detail::gj_regs<n, false, true>(m, snap, lane);
+                    if (act) {
+#pragma unroll
+                        for (uint32_t c = 0; c < n; ++c) invbuf[r + c * n] = m[n + c];
+                    }
+                }
+                __syncthreads();
+                if (has1) {
+                    float iv[n];
+#pragma unroll
+                    for (uint32_t k = 0; k < n; ++k) iv[k] = invbuf[r + k * n];
+                    const float *X = rj + K::OFF_L;
+                    constexpr uint32_t CW = (WC + 3) / 4;
+                    auto wq = [&](auto c0_tag) {
+                        constexpr uint32_t c0 = decltype(c0_tag)::value;
+                        constexpr uint32_t CNT = c0 >= WC ? 0 : (c0 + CW <= WC ? CW : WC - c0);
+                        if constexpr (CNT > 0) {
+                            float acc[CNT];
+#pragma unroll
+                            for (uint32_t c = 0; c < CNT; ++c) acc[c] = 0.0f;
+#pragma unroll
+                            for (uint32_t k = 0; k < n; k += 2) {
+#pragma unroll
+                                for (uint32_t c = 0; c < CNT; ++c) {
+                                    const float2 x2 = *reinterpret_cast<const float2 *>(X + k + (c0 + c) * n);
+                                    acc[c] = fma_rn(iv[k], x2.x, acc[c]);
+                                    acc[c] = fma_rn(iv[k + 1], x2.y, acc[c]);
+                                }
+                            }
+                            if (act) {
+#pragma unroll
+                                for (uint32_t c = 0; c < CNT; ++c) rj[K::OFF_W + r + (c0 + c) * n] = acc[c];
+                            }
+                        }
+                    };
+                    if (warp == 0) wq(std::integral_constant<uint32_t, 0>{});
+                    else if (warp == 1) wq(std::integral_constant<uint32_t, CW>{});
+                    else if (warp == 2) wq(std::integral_constant<uint32_t, 2 * CW>{});
+                    else wq(std::integral_constant<uint32_t, 3 * CW>{});
+                }
+            } else
             // phase 1: eliminate rows j = s (mod 2s)
             for_rows(s, s % (2 * s), [&](uint32_t j) {
                 float *rj = rec(j);
@@ -182,6 +239,67 @@ bcr_cluster_kernel(const BcrArgs a)
             stamp();
             cluster_sync();                                // W of every eliminated row visible cluster-wide
             stamp();
+            if (coop) {
+                const bool has2 = (2 * s == R) || ((cr * R) % (2 * s) == 0);
+                const uint32_t i = cr * R;
+                float *ri = rec(i);
+                const bool plus = warp >= 2;
+                const uint32_t half = warp & 1u;
+                const bool has_n = has2 && (plus ? i + s < N : i >= s);
+                constexpr uint32_t CH = n / 2;
+                float dacc[CH], nacc[CH], bacc = 0.0f;
+#pragma unroll
+                for (uint32_t c = 0; c < CH; ++c) { dacc[c] = 0.0f; nacc[c] = 0.0f; }
+                const uint32_t off_c = plus ? K::OFF_U : K::OFF_L;
+                if (has_n) {
+                    fetch_w(plus ? i + s : i - s, wm);
+                    __syncwarp();
+                    float crow[n];
+#pragma unroll
+                    for (uint32_t k = 0; k < n; ++k) crow[k] = ri[off_c + r + k * n];
+                    auto qpass = [&](auto c0_tag, auto side_tag) {
+                        constexpr uint32_t c0 = decltype(c0_tag)::value;
+                        constexpr bool minus_side = decltype(side_tag)::value;
+#pragma unroll
+                        for (uint32_t k = 0; k < n; k += 2) {
+#pragma unroll
+                            for (uint32_t c = 0; c < CH; ++c) {
+                                const float2 wl = *reinterpret_cast<const float2 *>(wm + k + (c0 + c) * n);
+                                const float2 wu = *reinterpret_cast<const float2 *>(wm + k + (n + c0 + c) * n);
+                                const float2 wd = minus_side ? wu : wl, wn = minus_side ? wl : wu;
+                                dacc[c] = fma_rn(crow[k], wd.x, dacc[c]); dacc[c] = fma_rn(crow[k + 1], wd.y, dacc[c]);
+                                nacc[c] = fma_rn(crow[k], wn.x, nacc[c]); nacc[c] = fma_rn(crow[k + 1], wn.y, nacc[c]);
+                            }
+                        }
+                    };
+                    if (!plus) { if (half == 0) qpass(std::integral_constant<uint32_t, 0>{}, std::true_type{}); else qpass(std::integral_constant<uint32_t, CH>{}, std::true_type{}); }
+                    else       { if (half == 0) qpass(std::integral_constant<uint32_t, 0>{}, std::false_type{}); else qpass(std::integral_constant<uint32_t, CH>{}, std::false_type{}); }
+                    if (half == 0) {
+#pragma unroll
+                        for (uint32_t k = 0; k < n; k += 2) {
+                            const float2 wb = *reinterpret_cast<const float2 *>(wm + k + 2 * n * n);
+                            bacc = fma_rn(crow[k], wb.x, bacc); bacc = fma_rn(crow[k + 1], wb.y, bacc);
+                        }
+                    }
+                }
+                __syncthreads();                           // every warp has read its coupling row before anyone rewrites L / U
+                const uint32_t c0r = half * CH;
+                if (has2 && act) {
+#pragma unroll
+                    for (uint32_t c = 0; c < CH; ++c) ri[off_c + r + (c0r + c) * n] = has_n ? -nacc[c] : 0.0f;
+                    if (!plus && has_n) {
+#pragma unroll
+                        for (uint32_t c = 0; c < CH; ++c) ri[K::OFF_D + r + (c0r + c) * n] -= dacc[c];
+                        if (half == 0) ri[K::OFF_B + r] -= bacc;
+                    }
+                }
+                __syncthreads();                           // minus side done with D and b; now the plus side
+                if (has2 && act && plus && has_n) {
+#pragma unroll
+                    for (uint32_t c = 0; c < CH; ++c) ri[K::OFF_D + r + (c0r + c) * n] -= dacc[c];
+                    if (half == 0) ri[K::OFF_B + r] -= bacc;
+                }
+            } else
             // phase 2: rows i = 0 (mod 2s) absorb their eliminated neighbours
             for_rows(s, 0, [&](uint32_t i) {
                 float *ri = rec(i);
