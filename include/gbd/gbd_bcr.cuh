@@ -154,7 +154,7 @@ bcr_cluster_kernel(const BcrArgs a)
                     float m[2 * n];
 #pragma unroll
                     for (uint32_t c = 0; c < n; ++c) {
-                        m[c] = rj[K::OFF_D + r + c * n];
+                        m[c] = act ? rj[K::OFF_D + r + c * n] : 0.0f;
                         m[n + c] = (c == r) ? 1.0f : 0.0f;
                     }
                     schur_detail::gj_regs<n, false, true>(m, snap, lane);
@@ -167,7 +167,7 @@ bcr_cluster_kernel(const BcrArgs a)
                 if (has1) {
                     float iv[n];
 #pragma unroll
-                    for (uint32_t k = 0; k < n; ++k) iv[k] = invbuf[r + k * n];
+                    for (uint32_t k = 0; k < n; ++k) iv[k] = act ? invbuf[r + k * n] : 0.0f;
                     const float *X = rj + K::OFF_L;
                     constexpr uint32_t CW = (WC + 3) / 4;
                     auto wq = [&](auto c0_tag) {
@@ -204,7 +204,7 @@ bcr_cluster_kernel(const BcrArgs a)
                 float m[2 * n];
 #pragma unroll
                 for (uint32_t c = 0; c < n; ++c) {
-                    m[c] = rj[K::OFF_D + r + c * n];
+                    m[c] = act ? rj[K::OFF_D + r + c * n] : 0.0f;
                     m[n + c] = (c == r) ? 1.0f : 0.0f;
                 }
                 schur_detail::gj_regs<n, false, true>(m, snap, lane);
@@ -256,7 +256,7 @@ bcr_cluster_kernel(const BcrArgs a)
                     __syncwarp();
                     float crow[n];
 #pragma unroll
-                    for (uint32_t k = 0; k < n; ++k) crow[k] = ri[off_c + r + k * n];
+                    for (uint32_t k = 0; k < n; ++k) crow[k] = act ? ri[off_c + r + k * n] : 0.0f;      // shadow lanes read nothing another lane writes
                     auto qpass = [&](auto c0_tag, auto side_tag) {
                         constexpr uint32_t c0 = decltype(c0_tag)::value;
                         constexpr bool minus_side = decltype(side_tag)::value;
@@ -314,7 +314,7 @@ bcr_cluster_kernel(const BcrArgs a)
                     constexpr bool minus_side = decltype(side_tag)::value;
                     float crow[n];
 #pragma unroll
-                    for (uint32_t k = 0; k < n; ++k) crow[k] = ri[off_c + r + k * n];
+                    for (uint32_t k = 0; k < n; ++k) crow[k] = act ? ri[off_c + r + k * n] : 0.0f;      // shadow lanes read nothing another lane writes
                     constexpr uint32_t CH = n / 2;                 // two passes over the columns keep the accumulators in registers
                     auto a_pass = [&](auto c0_tag) {
                         constexpr uint32_t c0 = decltype(c0_tag)::value;
@@ -372,7 +372,7 @@ bcr_cluster_kernel(const BcrArgs a)
             float m[2 * n];
 #pragma unroll
             for (uint32_t c = 0; c < n; ++c) {
-                m[c] = r0[K::OFF_D + r + c * n];
+                m[c] = act ? r0[K::OFF_D + r + c * n] : 0.0f;
                 m[n + c] = (c == r) ? 1.0f : 0.0f;
             }
             schur_detail::gj_regs<n, false, true>(m, snap, lane);
