@@ -43,8 +43,23 @@ struct PcgArgs {
     uint32_t max_iter;
     T exit_tol;
     uint32_t use_tma;  // 0: plain loads (unaligned pointers)
+    uint32_t *host_result = nullptr;   // nullable: mapped pinned mirror {iters, flag} of system 0 (the linsys window reads it
+                                       // after one stream wait instead of two device-to-host copies)
     uint32_t *dbg = nullptr;   // timeline build only (gbd_pcg_set_debug_buffer): per-thread %clock stamps
 };
+
+// iteration count and exit flag of system `sys` (pcg.cuh:212-215), plus the optional host mirror
+template <typename T>
+__device__ __forceinline__ void store_result(const PcgArgs<T> &a, uint32_t sys, uint32_t iter, uint8_t max_iter_exit)
+{
+    a.iters[sys] = iter;
+    a.max_iter_exit[sys] = max_iter_exit;
+    if (a.host_result && sys == 0) {
+        volatile uint32_t *h = a.host_result;
+        h[1] = max_iter_exit;
+        h[0] = iter;
+    }
+}
 
 template <typename T, uint32_t n, uint32_t N, uint32_t C, bool REGS>
 struct ClusterPcg {
@@ -294,8 +309,7 @@ pcg_cluster_kernel(const PcgArgs<T> a)
             if (a.p_out) a.p_out[voff + t] = p;
         }
         if (cr == 0 && t == 0) {
-            a.iters[sys] = iter;
-            a.max_iter_exit[sys] = max_iter_exit;
+            store_result(a, sys, iter, max_iter_exit);
         }
         __syncthreads();   // smem of this system is dead before the next one is staged
     }

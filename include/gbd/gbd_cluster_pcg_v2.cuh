@@ -422,8 +422,7 @@ pcg_cluster_kernel_v2(const PcgArgs<T> a)
             if (a.p_out) a.p_out[o] = p;
         }
         if (cr == 0 && t == 0) {
-            a.iters[sys] = iter;
-            a.max_iter_exit[sys] = max_iter_exit;
+            store_result(a, sys, iter, max_iter_exit);
         }
         __syncthreads();
     }

@@ -339,8 +339,7 @@ __device__ __forceinline__ void pcg_cluster_v3_run(const PcgArgs<float> &a, unsi
             if (a.p_out) { a.p_out[o + j0] = p0; a.p_out[o + j1] = p1; }
         }
         if (cr == 0 && t == 0) {
-            a.iters[sys] = iter;
-            a.max_iter_exit[sys] = max_iter_exit;
+            store_result(a, sys, iter, max_iter_exit);
         }
         cta_sync();
     }

@@ -348,8 +348,7 @@ __device__ __forceinline__ void pcg_cluster_v4_run(const PcgArgs<float> &a, unsi
             if (a.p_out) a.p_out[o] = p;
         }
         if (cr == 0 && t == 0) {
-            a.iters[sys] = iter;
-            a.max_iter_exit[sys] = max_iter_exit;
+            store_result(a, sys, iter, max_iter_exit);
         }
         cta_sync();
     }

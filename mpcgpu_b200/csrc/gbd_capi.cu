@@ -296,7 +296,8 @@ int launch_grid(Variant &v, uint32_t batch, const T *S, const T *P, const T *g, 
 
 template <typename T>
 int launch(uint32_t n, uint32_t N, uint32_t batch, const T *S, const T *P, const T *g, T *lam, T *r, T *p,
-           uint32_t *iters, uint8_t *flag, uint32_t max_iter, T tol, cudaStream_t st, bool no_tma = false)
+           uint32_t *iters, uint8_t *flag, uint32_t max_iter, T tol, cudaStream_t st, bool no_tma = false,
+           uint32_t *host_result = nullptr)
 {
     if (!S || !P || !g || !lam || !iters || !flag || batch == 0 || N < 2 || n == 0) return GBD_PCG_ERR_BADARG;
     Variant *v = find_variant(n, N, sizeof(T) == 8, batch > 1);
@@ -323,6 +324,7 @@ int launch(uint32_t n, uint32_t N, uint32_t batch, const T *S, const T *P, const
     a.iters = iters; a.max_iter_exit = flag; a.batch = batch; a.max_iter = max_iter; a.exit_tol = tol;
     a.use_tma = (!no_tma && (((uintptr_t)S | (uintptr_t)P) & 15u) == 0) ? 1u : 0u;
     a.dbg = g_dbg;
+    a.host_result = host_result;
 
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute at[1];
@@ -350,7 +352,12 @@ struct gbd_pcg_plan {
     uint8_t *d_flag;
     uint32_t *h_iters_pin;   // pinned + mapped result slots for the zero-copy path
     uint8_t *h_flag_pin;
+    uint32_t *z_iters;       // their device aliases
+    uint8_t *z_flag;
     cudaStream_t st;
+    // device aliases of caller buffers this plan has already seen (a pinned buffer keeps its alias for as long as it stays
+    // registered; unregistering a buffer while a plan that has used it is alive is not supported)
+    struct Alias { const void *host; const void *dev; } alias[512];
 };
 
 extern "C" {
@@ -434,22 +441,29 @@ int gbd_pcg_linsys_f32(uint32_t n, uint32_t N, const float *d_S, const float *d_
     // same observable window as include/pcg/sqp.cuh:224-241 (device idle before, both results on the host and the device
     // idle after), but the two blocking cudaMemcpy + cudaDeviceSynchronize become two async copies into pinned slots and
     // one spin on the stream: ~15 us less host-side latency per SQP iteration
-    static uint32_t *pin = nullptr;                     // [0] iters, [1] flag byte
+    static uint32_t *pin = nullptr, *pin_dev = nullptr;     // [0] iters, [1] flag: pinned + mapped, written by the kernel itself
     if (!pin) {
         std::lock_guard<std::mutex> lk(g_mu);
-        if (!pin) CK(cudaHostAlloc((void **)&pin, 2 * sizeof(uint32_t), cudaHostAllocDefault));
+        if (!pin) {
+            CK(cudaHostAlloc((void **)&pin, 2 * sizeof(uint32_t), cudaHostAllocMapped));
+            CK(cudaHostGetDevicePointer((void **)&pin_dev, pin, 0));
+        }
     }
     timespec t0, t1;
     CK(cudaDeviceSynchronize());
     clock_gettime(CLOCK_MONOTONIC, &t0);
+    Variant *v = find_variant(n, N, false, false);
+    const bool mirror = v && v->mode != 4;              // the cluster kernels write the two results into the mapped slots
     int rc = launch<float>(n, N, 1, d_S, d_Pinv, d_gamma, d_lambda, d_r, d_p, d_iters, d_max_iter_exit, max_iter,
-                           exit_tol, (cudaStream_t)0);
+                           exit_tol, (cudaStream_t)0, false, mirror ? pin_dev : nullptr);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(&pin[0], d_iters, sizeof(uint32_t), cudaMemcpyDeviceToHost, (cudaStream_t)0));
-    CK(cudaMemcpyAsync(&pin[1], d_max_iter_exit, sizeof(uint8_t), cudaMemcpyDeviceToHost, (cudaStream_t)0));
+    if (!mirror) {
+        CK(cudaMemcpyAsync(&pin[0], d_iters, sizeof(uint32_t), cudaMemcpyDeviceToHost, (cudaStream_t)0));
+        CK(cudaMemcpyAsync(&pin[1], d_max_iter_exit, sizeof(uint8_t), cudaMemcpyDeviceToHost, (cudaStream_t)0));
+    }
     CK(spin_sync((cudaStream_t)0));
     *h_iters = pin[0];
-    *h_max_iter_exit = *reinterpret_cast<uint8_t *>(&pin[1]);
+    *h_max_iter_exit = (uint8_t)pin[1];
     clock_gettime(CLOCK_MONOTONIC, &t1);
     if (elapsed_us) *elapsed_us = 1e6 * (double)(t1.tv_sec - t0.tv_sec) + 1e-3 * (double)(t1.tv_nsec - t0.tv_nsec);
     return GBD_PCG_OK;
@@ -477,7 +491,9 @@ int gbd_pcg_plan_create(uint32_t n, uint32_t N, uint32_t batch, int is_f64, gbd_
         (e = cudaMalloc((void **)&p->d_iters, sizeof(uint32_t) * batch)) != cudaSuccess ||
         (e = cudaMalloc((void **)&p->d_flag, batch)) != cudaSuccess ||
         (e = cudaHostAlloc((void **)&p->h_iters_pin, sizeof(uint32_t) * batch, cudaHostAllocMapped)) != cudaSuccess ||
-        (e = cudaHostAlloc((void **)&p->h_flag_pin, batch, cudaHostAllocMapped)) != cudaSuccess) {
+        (e = cudaHostAlloc((void **)&p->h_flag_pin, batch, cudaHostAllocMapped)) != cudaSuccess ||
+        (e = cudaHostGetDevicePointer((void **)&p->z_iters, p->h_iters_pin, 0)) != cudaSuccess ||
+        (e = cudaHostGetDevicePointer((void **)&p->z_flag, p->h_flag_pin, 0)) != cudaSuccess) {
         gbd_pcg_plan_destroy(p);
         return cuda_fail(e);
     }
@@ -523,12 +539,17 @@ int plan_solve_host(gbd_pcg_plan *p, const T *hS, const T *hP, const T *hg, T *h
     if (!p || !hS || !hP || !hg || !hl || !h_iters || !h_flag) return GBD_PCG_ERR_BADARG;
     if (p->f64 != (sizeof(T) == 8)) return GBD_PCG_ERR_BADARG;
     if (zerocopy_mode() != 0) {
-        const T *zS = (const T *)device_alias(hS), *zP = (const T *)device_alias(hP), *zg = (const T *)device_alias(hg);
-        T *zl = (T *)device_alias(hl);
+        auto alias_of = [&](const void *h) -> const void * {
+            gbd_pcg_plan::Alias &slot = p->alias[((uintptr_t)h >> 8) & 511u];
+            if (slot.host == h) return slot.dev;
+            const void *d = device_alias(h);
+            if (d) { slot.host = h; slot.dev = d; }
+            return d;
+        };
+        const T *zS = (const T *)alias_of(hS), *zP = (const T *)alias_of(hP), *zg = (const T *)alias_of(hg);
+        T *zl = (T *)alias_of(hl);
         if (zS && zP && zg && zl) {
-            uint32_t *zi = nullptr; uint8_t *zf = nullptr;
-            CK(cudaHostGetDevicePointer((void **)&zi, p->h_iters_pin, 0));
-            CK(cudaHostGetDevicePointer((void **)&zf, p->h_flag_pin, 0));
+            uint32_t *zi = p->z_iters; uint8_t *zf = p->z_flag;
             int rc = launch<T>(p->n, p->N, p->batch, zS, zP, zg, zl, (T *)nullptr, (T *)nullptr, zi, zf, max_iter, tol, p->st,
                                zerocopy_mode() == 2);
             if (rc) return rc;
