@@ -177,15 +177,31 @@ __device__ __forceinline__ T chain_padded(const T (&m)[3 * n], const T *__restri
     return acc;
 }
 
-template <typename T, uint32_t n, uint32_t N, uint32_t C, uint32_t MINB, bool PROF = false>
-__global__ void __launch_bounds__(ClusterPcg2<T, n, N, C>::NT, MINB)
-pcg_cluster_kernel_v2(const PcgArgs<T> a)
+// mbarrier set-up of one CTA; the caller follows it with a CTA barrier and cluster_sync()
+template <typename T, uint32_t n, uint32_t N, uint32_t C>
+__device__ __forceinline__ void pcg_cluster_v2_init(unsigned char *smem_raw)
 {
+    using K = ClusterPcg2<T, n, N, C>;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + K::OFF_BAR);
+    if (threadIdx.x == 0) {
+        mbar_init(bars, 1);
+        mbar_init(bars + 1, 1);
+        mbar_init(bars + 2, 1);
+        fence_mbar_init();
+    }
+}
+
+// Solves systems first_sys, first_sys + sys_stride, ... < a.batch with this cluster.  Called by threads 0 .. NT-1 of every CTA of
+// the cluster (EXACT_BLOCK: the launch carries exactly NT threads and the plain CTA barrier is used; otherwise a named barrier
+// over NT threads, so the drop-in pcg<T,n,N> can run it under a larger caller-chosen block).
+template <typename T, uint32_t n, uint32_t N, uint32_t C, bool PROF, bool EXACT_BLOCK>
+__device__ __forceinline__ void pcg_cluster_v2_run(const PcgArgs<T> &a, unsigned char *smem_raw, uint32_t first_sys, uint32_t sys_stride)
+{
+    auto cta_sync = [&]() { if constexpr (EXACT_BLOCK) __syncthreads(); else named_bar_sync(2, ClusterPcg2<T, n, N, C>::NT); };
     using K = ClusterPcg2<T, n, N, C>;
     constexpr uint32_t R = K::R, W = K::W, TILE = K::TILE, G = K::G, XS = K::XS, VEC = K::VEC, NT = K::NT;
     constexpr uint32_t HCH = XS / VEC;             // 16-byte messages per boundary row
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + K::OFF_BAR);
     uint64_t *barT = bars, *barA = bars + 1, *barB = bars + 2;
     T *sS = reinterpret_cast<T *>(smem_raw + K::OFF_S);
@@ -207,7 +223,6 @@ pcg_cluster_kernel_v2(const PcgArgs<T> a)
     const uint32_t k = group_live ? g : R - 1;     // local knot row (clamped for padding lanes)
     const bool is_row = group_live && j < n;
     const uint32_t cr = cluster_ctarank();
-    const uint32_t cid = cluster_idx(), ncl = cluster_count();
     const uint32_t b = cr * R + k;
     const bool has_left = cr > 0, has_right = cr + 1 < C;
     const uint32_t left = has_left ? cr - 1 : cr, right = has_right ? cr + 1 : cr;
@@ -254,17 +269,8 @@ pcg_cluster_kernel_v2(const PcgArgs<T> a)
         }
     };
 
-    if (t == 0) {
-        mbar_init(barT, 1);
-        mbar_init(barA, 1);
-        mbar_init(barB, 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-    cluster_sync();   // all CTAs resident, all mbarriers initialised, before any DSMEM traffic
-
     uint32_t phT = 0, phA = 0, phB = 0;
-    for (uint32_t sys = cid; sys < a.batch; sys += ncl) {
+    for (uint32_t sys = first_sys; sys < a.batch; sys += sys_stride) {
         const size_t moff = ((size_t)sys * N + (size_t)cr * R) * TILE;
         const size_t vbase = (size_t)sys * N * n;
         const T *gS = a.S + moff, *gP = a.Pinv + moff;
@@ -302,12 +308,12 @@ pcg_cluster_kernel_v2(const PcgArgs<T> a)
         }
         if (tma) mbar_wait(barT, phT);
         phT ^= 1u;
-        __syncthreads();
+        cta_sync();
         if (cr == 0)
             for (uint32_t i = t; i < n * n; i += NT) { sS[i] = T(0); sP[i] = T(0); }
         if (cr == C - 1)
             for (uint32_t i = t; i < n * n; i += NT) { sS[(R - 1) * TILE + 2 * n * n + i] = T(0); sP[(R - 1) * TILE + 2 * n * n + i] = T(0); }
-        __syncthreads();
+        cta_sync();
 
         // this thread's rows of S and Pinv live in registers for the whole solve
         T ms[W], mp[W];
@@ -330,7 +336,7 @@ pcg_cluster_kernel_v2(const PcgArgs<T> a)
         ship(part_e, barA, xr + (R + 1) * XS, xr, false, halo_bytes);
         mbar_wait(barA, phA);
         phA ^= 1u;
-        __syncthreads();
+        cta_sync();
         // ---- r~ = Pinv*r ; p = r~ ; eta = r.r~                             (pcg.cuh:130-149)
         T rt = chain_padded<T, n, XS>(mp, wr);
         {
@@ -361,7 +367,7 @@ pcg_cluster_kernel_v2(const PcgArgs<T> a)
             }
         };
         for (; iter < a.max_iter; ++iter) {
-            __syncthreads();
+            cta_sync();
             stamp(0, p);
             // ---- upsilon = S*p ; v = p.upsilon                             (pcg.cuh:156-167)
             ups = chain_padded<T, n, XS>(ms, wp);
@@ -386,7 +392,7 @@ pcg_cluster_kernel_v2(const PcgArgs<T> a)
             if (is_row) *own_r = r;
             if (own_lhalo && has_left) xr[j] = fma_rn(-alpha, hu[j], xr[j]);
             if (own_rhalo && has_right) xr[(R + 1) * XS + j] = fma_rn(-alpha, hu[XS + j], xr[(R + 1) * XS + j]);
-            __syncthreads();
+            cta_sync();
             stamp(6, r);
             // ---- r~ = Pinv*r ; eta' = r.r~                                 (:180-193)
             rt = chain_padded<T, n, XS>(mp, wr);
@@ -424,10 +430,22 @@ pcg_cluster_kernel_v2(const PcgArgs<T> a)
         if (cr == 0 && t == 0) {
             store_result(a, sys, iter, max_iter_exit);
         }
-        __syncthreads();
+        cta_sync();
     }
-    cluster_sync();
     (void)first_row; (void)last_row;
+}
+
+// C-ABI kernel: persistent clusters looping over a batch of systems
+template <typename T, uint32_t n, uint32_t N, uint32_t C, uint32_t MINB, bool PROF = false>
+__global__ void __launch_bounds__(ClusterPcg2<T, n, N, C>::NT, MINB)
+pcg_cluster_kernel_v2(const PcgArgs<T> a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    pcg_cluster_v2_init<T, n, N, C>(smem_raw);
+    __syncthreads();
+    cluster_sync();   // all CTAs resident, all mbarriers initialised, before any DSMEM traffic
+    pcg_cluster_v2_run<T, n, N, C, PROF, true>(a, smem_raw, cluster_idx(), cluster_count());
+    cluster_sync();   // no CTA leaves while a peer may still write into its shared memory
 }
 
 }  // namespace gbd
