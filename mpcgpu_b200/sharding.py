@@ -72,19 +72,27 @@ class ShardedStep:
     one StepPlan run on the local shard (assembly -> solve -> dz, no host round trip) + the one all-gather of the
     per-trajectory max_iter_exit flags per outer step."""
 
-    def __init__(self, n: int, m: int, N: int, batch: int, world: int, rank: int):
-        from . import solver
+    def __init__(self, n: int, m: int, N: int, batch: int, world: int, rank: int, plan_factory=None, direct_fallback: bool = False):
+        """plan_factory(n, m, N, local_batch) -> object with run(...) and device_flags(); defaults to solver.StepPlan (the CPU
+        tests of the host logic inject a stand-in, there is no CPU solver)."""
         self.n, self.m, self.N, self.batch, self.world, self.rank = n, m, N, batch, world, rank
         self.lo, self.hi = shard_range(batch, world, rank)
         self.local = self.hi - self.lo
-        self.plan = solver.StepPlan(n, m, N, self.local) if self.local else None
+        self.direct_fallback = direct_fallback
+        if plan_factory is None:
+            from . import solver
+            plan_factory = solver.StepPlan
+        self.plan = plan_factory(n, m, N, self.local) if self.local else None
 
     def step(self, d_G, d_C, d_g, d_c, rho, d_lambda, d_dz, max_iter: int, exit_tol: float):
-        """Returns the [batch] uint8 max_iter_exit vector of the whole batch (on this rank's GPU)."""
+        """Returns the [batch] uint8 max_iter_exit vector of the whole batch (on this rank's device)."""
         import torch
         if self.plan is not None:
-            self.plan.run(d_G, d_C, d_g, d_c, rho, d_lambda, d_dz, max_iter, exit_tol)
+            if self.direct_fallback:
+                self.plan.run(d_G, d_C, d_g, d_c, rho, d_lambda, d_dz, max_iter, exit_tol, direct_fallback=True)
+            else:
+                self.plan.run(d_G, d_C, d_g, d_c, rho, d_lambda, d_dz, max_iter, exit_tol)
             flags = self.plan.device_flags()
         else:
-            flags = torch.zeros(0, dtype=torch.uint8, device="cuda")
+            flags = torch.zeros(0, dtype=torch.uint8, device=d_lambda.device)
         return gather_converged(flags, self.batch, self.world, self.rank)
