@@ -10,7 +10,7 @@ sys.path.insert(0, ROOT)
 import mpcgpu_b200 as m  # noqa: E402
 from mpcgpu_b200 import synth  # noqa: E402
 
-n, N = 14, int(os.environ.get("KNOTS", "128"))
+n, N = int(os.environ.get("STATE", "14")), int(os.environ.get("KNOTS", "128"))
 B = int(os.environ.get("BATCH", "256"))
 d = synth.make_systems(n, N, batch=max(B, 8), seed=3)
 S, P, g = (torch.from_numpy(d[k]).cuda() for k in ("S", "Pinv", "gamma"))
@@ -18,7 +18,8 @@ it = torch.zeros(B, dtype=torch.int32, device="cuda")
 fl = torch.zeros(B, dtype=torch.uint8, device="cuda")
 for i in range(int(os.environ.get("SINGLES", "24"))):
     lam = torch.zeros(n * N, device="cuda")
-    m.pcg_launch(n, N, S[i % 8], P[i % 8], g[i % 8], lam, None, None, None, None, it, fl, 167, 1e-4)
+    m.pcg_launch(n, N, S[i % 8], P[i % 8], g[i % 8], lam, None, None, None, None, it, fl, int(os.environ.get("CAP", "167")),
+                 float(os.environ.get("TOL", "1e-4")))
 torch.cuda.synchronize()
 if B > 1:
     for _ in range(2):
