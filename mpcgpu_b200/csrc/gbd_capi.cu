@@ -442,7 +442,7 @@ int gbd_pcg_linsys_f32(uint32_t n, uint32_t N, const float *d_S, const float *d_
     // idle after), but the two blocking cudaMemcpy + cudaDeviceSynchronize become two async copies into pinned slots and
     // one spin on the stream: ~15 us less host-side latency per SQP iteration
     static uint32_t *pin = nullptr, *pin_dev = nullptr;     // [0] iters, [1] flag: pinned + mapped, written by the kernel itself
-    if (!pin) {
+    {   // (the window itself is one caller at a time by construction: it brackets the legacy default stream, like the reference's)
         std::lock_guard<std::mutex> lk(g_mu);
         if (!pin) {
             CK(cudaHostAlloc((void **)&pin, 2 * sizeof(uint32_t), cudaHostAllocMapped));
@@ -776,7 +776,7 @@ int bcr_launch(uint32_t batch, const float *S, const float *g, float *lam, cudaS
     auto kern = gbd::bcr_cluster_kernel<n, N, C, MINB, PROF>;
     static bool prepared = false;
     static int max_clusters = 0;
-    if (!prepared) {
+    {
         std::lock_guard<std::mutex> lk(g_mu);
         if (!prepared) {
             if (K::SMEM_BYTES > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES));
