@@ -46,6 +46,8 @@ struct PcgArgs {
     uint32_t *host_result = nullptr;   // nullable: mapped pinned mirror {iters, flag} of system 0 (the linsys window reads it
                                        // after one stream wait instead of two device-to-host copies)
     uint32_t *dbg = nullptr;   // timeline build only (gbd_pcg_set_debug_buffer): per-thread %clock stamps
+    uint32_t *work_counter = nullptr;  // nullable, zeroed before the launch: batched launches of the v5 kernel draw each cluster's
+                                       // next system from it (first come, first served) instead of a fixed stride
 };
 
 // iteration count and exit flag of system `sys` (pcg.cuh:212-215), plus the optional host mirror

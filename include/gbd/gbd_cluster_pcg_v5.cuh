@@ -44,6 +44,7 @@ struct ClusterPcg5 {
     static constexpr uint32_t PK_HR = 3 * N, PK_H0 = PK_HR + 2 * XS, PK_HU = PK_H0 + 2 * XS, PK_HT = PK_HU + 2 * XS;
     static constexpr uint32_t PK_COUNT = PK_HT + 2 * XS;
     static constexpr size_t OFF_BAR = 0;
+    static constexpr size_t OFF_NEXT = 8;                // one packet {next system, solve sequence number} (work_counter mode)
     static constexpr size_t OFF_PK = 16;
     static constexpr size_t OFF_XP = OFF_PK + sizeof(uint64_t) * PK_COUNT;
     static constexpr size_t OFF_XR = OFF_XP + align16(sizeof(T) * XLEN);
@@ -59,6 +60,7 @@ __device__ __forceinline__ void pcg_cluster_v5_init(unsigned char *smem_raw)
     uint64_t *pk = reinterpret_cast<uint64_t *>(smem_raw + K::OFF_PK);
     for (uint32_t i = threadIdx.x; i < K::PK_COUNT; i += blockDim.x) pk[i] = 0ull;      // epoch 0 is never sent
     if (threadIdx.x == 0) {
+        *reinterpret_cast<uint64_t *>(smem_raw + K::OFF_NEXT) = 0ull;
         mbar_init(reinterpret_cast<uint64_t *>(smem_raw + K::OFF_BAR), 1);
         fence_mbar_init();
     }
@@ -66,6 +68,10 @@ __device__ __forceinline__ void pcg_cluster_v5_init(unsigned char *smem_raw)
 
 // Solves systems first_sys, first_sys + sys_stride, ... < a.batch with this cluster.  Called by threads 0 .. NT-1 of
 // every CTA of the cluster, after pcg_cluster_v5_init + CTA barrier + cluster_sync.
+// With a.work_counter (zero before the launch; sys_stride = number of clusters) only the FIRST system is fixed: while a
+// solve runs, CTA 0 draws the cluster's next system from the counter and posts it to every CTA as one more packet, so
+// clusters that meet short solves take more systems (iteration counts differ per system; a fixed stride leaves the
+// tail of the batch to whichever clusters happened to draw the long ones).
 template <uint32_t n, uint32_t N, uint32_t C, bool STAGE, bool EXACT_BLOCK>
 __device__ __forceinline__ void pcg_cluster_v5_run(const PcgArgs<float> &a, unsigned char *smem_raw, uint32_t first_sys,
                                                    uint32_t sys_stride)
@@ -148,8 +154,10 @@ __device__ __forceinline__ void pcg_cluster_v5_run(const PcgArgs<float> &a, unsi
         return x;
     };
 
-    uint32_t phT = 0, ep = 0;
-    for (uint32_t sys = first_sys; sys < a.batch; sys += sys_stride) {
+    const bool draw = a.work_counter != nullptr;
+    const uint32_t next_u = smem_u32(smem_raw + K::OFF_NEXT);
+    uint32_t phT = 0, ep = 0, seq = 0;
+    for (uint32_t sys = first_sys; sys < a.batch;) {
         const size_t moff = ((size_t)sys * N + (size_t)cr * R) * TILE;
         const size_t vbase = (size_t)sys * N * n;
         const T *gS = a.S + moff, *gP = a.Pinv + moff;
@@ -243,6 +251,14 @@ __device__ __forceinline__ void pcg_cluster_v5_run(const PcgArgs<float> &a, unsi
         send_edge(K::PK_H0, rt0, rt1, ep);
         send_part(K::PK_PART0, r0, rt0, r1, rt1, ep);
         T eta = gather(K::PK_PART0, K::PK_H0, ep, e0, e1);
+        ++seq;
+        if (draw && cr == 0 && t == 0) {
+            // every CTA has entered this solve (its partials arrived), so it has consumed the previous post: the one
+            // slot can be overwritten.  Posted now, read after the solve: the counter's round trip is off the path.
+            const uint32_t nx = atomicAdd(a.work_counter, 1u) + sys_stride;
+#pragma unroll
+            for (uint32_t c = 0; c < C; ++c) st_packet<false>(map_to_cta(next_u, c), __uint_as_float(nx), seq);
+        }
         T p0 = rt0, p1 = rt1, u0 = T(0), u1 = T(0);
         T ph0 = e0, ph1 = e1;                              // register copies of the neighbour's boundary p elements
         if (act) { own_p[j0] = p0; own_p[j1] = p1; }
@@ -296,6 +312,17 @@ __device__ __forceinline__ void pcg_cluster_v5_run(const PcgArgs<float> &a, unsi
             store_result(a, sys, iter, max_iter_exit);
         }
         cta_sync();
+        if (draw) {
+            uint64_t q;
+            uint32_t spins = 0;
+            do {
+                q = ld_packet(next_u);
+                if (++spins > (1u << 26)) __trap();          // a lost post would otherwise hang the GPU
+            } while (!packet_ok(q, seq));
+            sys = __float_as_uint(packet_val(q));
+        } else {
+            sys += sys_stride;
+        }
     }
 }
 

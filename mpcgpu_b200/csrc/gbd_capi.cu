@@ -325,6 +325,24 @@ int launch(uint32_t n, uint32_t N, uint32_t batch, const T *S, const T *P, const
     a.use_tma = (!no_tma && (((uintptr_t)S | (uintptr_t)P) & 15u) == 0) ? 1u : 0u;
     a.dbg = g_dbg;
     a.host_result = host_result;
+    if constexpr (sizeof(T) == 4) {
+        // v5 with more systems than resident clusters: clusters draw their next system from a counter (zeroed on this
+        // stream ahead of the launch) -- GBD_PCG_STATIC_BATCH=1 keeps the fixed stride (A/B)
+        static const bool static_batch = [] { const char *e = getenv("GBD_PCG_STATIC_BATCH"); return e && atoi(e) != 0; }();
+        if ((v->mode == 11 || v->mode == 12) && batch > nclusters && !static_batch) {
+            constexpr uint32_t SLOTS = 256;                  // launches in flight at once before a slot is reused
+            static uint32_t *counters = nullptr;
+            static uint32_t next_slot = 0;
+            uint32_t slot;
+            {
+                std::lock_guard<std::mutex> lk(g_mu);
+                if (!counters) CK(cudaMalloc((void **)&counters, SLOTS * sizeof(uint32_t)));
+                slot = next_slot++ % SLOTS;
+            }
+            CK(cudaMemsetAsync(counters + slot, 0, sizeof(uint32_t), st));
+            a.work_counter = counters + slot;
+        }
+    }
 
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute at[1];
