@@ -137,6 +137,28 @@ def test_batched_equals_single_and_oracle(torch_cuda, capi, oracle_pcg):
     assert len(set(want["iters"].tolist())) > 1          # systems really differ
 
 
+def test_batched_uneven_iteration_counts(torch_cuda, capi, oracle_pcg):
+    """Right-hand sides scaled over six decades: solves of 1 .. cap iterations in one launch, more systems than resident
+    clusters -- the clusters draw systems from the work counter in a data-dependent order; every system must still equal
+    the oracle bit for bit and land in its own slot."""
+    import mpcgpu_b200 as m
+    torch = torch_cuda
+    n, N, B, cap, tol = 14, 32, 260, 60, 1e-4
+    d = synth.make_systems(n, N, batch=B, seed=77)
+    scale = (10.0 ** np.random.default_rng(5).uniform(-4.0, 2.0, size=B)).astype(np.float32)
+    gam = (d["gamma"] * scale[:, None]).astype(np.float32)
+    S, P, g, lam = (_dev(torch, x) for x in (d["S"], d["Pinv"], gam, d["lambda0"]))
+    it = torch.zeros(B, dtype=torch.int32, device="cuda")
+    fl = torch.zeros(B, dtype=torch.uint8, device="cuda")
+    m.solve_batched(n, N, B, S, P, g, lam, it, fl, cap, tol)
+    torch.cuda.synchronize()
+    want = oracle_pcg.pcg_batched(d["S"], d["Pinv"], gam, d["lambda0"], n, N, B, cap, tol)
+    assert np.array_equal(it.cpu().numpy().astype(np.uint32), want["iters"])
+    assert np.array_equal(fl.cpu().numpy().astype(bool), want["max_iter_exit"])
+    assert np.array_equal(lam.cpu().numpy(), want["lam"])
+    assert want["iters"].min() <= 5 and want["max_iter_exit"].any()      # from almost-converged to capped
+
+
 def test_full_size_batch_properties(torch_cuda, capi, oracle_pcg):
     """BASELINE config 4 size (1024 x N=128): too big for the oracle in seconds, so check
     size-independent properties: every system's fp64 residual is small, iteration counts equal the
