@@ -95,7 +95,9 @@ int gbd_pcg_linsys_f32(uint32_t n, uint32_t N, const float *d_S, const float *d_
  * Many independent systems in one launch (new capability; the reference has no batched path).
  * Arrays carry a leading [batch] dimension; d_iters / d_max_iter_exit have `batch` entries.
  * System i is solved exactly as gbd_pcg_solve_f32 would solve it alone (bit-identical).
- * d_r / d_p may be NULL.
+ * d_r / d_p may be NULL.  With more systems than the GPU keeps clusters resident, clusters take the systems first come,
+ * first served (a 4-byte device counter zeroed on `stream` ahead of the launch); the environment variable
+ * GBD_PCG_STATIC_BATCH=1 restores a fixed stride.  Which cluster solves a system never changes its result.
  */
 int gbd_pcg_solve_batched_f32(uint32_t n, uint32_t N, uint32_t batch, const float *d_S, const float *d_Pinv,
                               const float *d_gamma, float *d_lambda, float *d_r, float *d_p,
