@@ -83,17 +83,13 @@ struct GridPcg {
     // a partial per consumer, so no line is ever polled by more than one CTA: with one shared copy all CTAS x NT
     // threads spin on the same N/16 lines and the L2 slice serialises them (measured, tools/micro/l2_exchange.cu:
     // 7200 -> 3000 cycles per all-gather at 128 CTAs, N = 256).
-    // PREG: S and Pinv of R knot rows do not both fit in shared memory -> the Pinv row of each thread lives in registers
-    // (3n values; staged through the S buffer first), the S rows in shared memory.  n = 64, R = 4: 64 CTAs instead of 128,
-    // i.e. half the consumers in every all-gather, and a register-fed second chain.
-    static constexpr bool PREG = !SMALL && sizeof(T) == 4 && n % 4 == 0 && 2 * R * TILE * sizeof(T) > 200 * 1024;
     static constexpr size_t REGION_WORDS = (size_t)PW * (N + 2 * n);
     static constexpr size_t PH_WORDS = REGION_WORDS * CTAS;
     static constexpr size_t WS_WORDS = 2 * PH_WORDS;
     static constexpr size_t align16(size_t x) { return (x + 15) / 16 * 16; }
     static constexpr size_t OFF_BAR = 0;
     static constexpr size_t OFF_S = 16;
-    static constexpr size_t OFF_P = PREG ? OFF_S : OFF_S + align16(sizeof(T) * R * TILE);
+    static constexpr size_t OFF_P = OFF_S + align16(sizeof(T) * R * TILE);
     static constexpr size_t OFF_XP = OFF_P + align16(sizeof(T) * R * TILE);
     static constexpr size_t OFF_XR = OFF_XP + align16(sizeof(T) * XLEN);
     static constexpr size_t OFF_HU = OFF_XR + align16(sizeof(T) * XLEN);
@@ -131,25 +127,6 @@ __device__ __forceinline__ T chain_padded_smem(const T *__restrict__ mrow, const
         }
 #pragma unroll 4
         for (uint32_t c = n / CB * CB; c < n; ++c) acc = fma_rn(mrow[(blk * n + c) * n], xw[blk * XS + c], acc);
-    }
-    return acc;
-}
-
-// the same chain with the matrix row in registers and the window read 128 bits at a time as it is consumed (n % 4 == 0)
-template <uint32_t n, uint32_t XS>
-__device__ __forceinline__ float chain_padded_mreg(const float (&m)[3 * n], const float *__restrict__ xw)
-{
-    float acc = 0.0f;
-#pragma unroll
-    for (uint32_t blk = 0; blk < 3; ++blk) {
-#pragma unroll
-        for (uint32_t c0 = 0; c0 < n; c0 += 4) {
-            const float4 f = *reinterpret_cast<const float4 *>(xw + blk * XS + c0);
-            acc = fma_rn(m[blk * n + c0], f.x, acc);
-            acc = fma_rn(m[blk * n + c0 + 1], f.y, acc);
-            acc = fma_rn(m[blk * n + c0 + 2], f.z, acc);
-            acc = fma_rn(m[blk * n + c0 + 3], f.w, acc);
-        }
     }
     return acc;
 }
@@ -309,26 +286,7 @@ __device__ __forceinline__ uint32_t pcg_grid_body(const T *__restrict__ gS_all, 
         fence_mbar_init();
     }
     __syncthreads();
-    // one band-row block (R tiles) into the tile buffer: TMA bulk copies on barT, or plain loads
-    auto stage_one = [&](const T *src) {
-        if (tma) {
-            if (t == 0) {
-                constexpr uint32_t total = (uint32_t)(sizeof(T) * R * TILE);
-                constexpr uint32_t CHB = 16384;
-                fence_proxy_async();
-                mbar_arrive_expect_tx(barT, total);
-                for (uint32_t o = 0; o < total; o += CHB) {
-                    const uint32_t len = total - o < CHB ? total - o : CHB;
-                    tma_bulk_g2s(reinterpret_cast<unsigned char *>(sS) + o, reinterpret_cast<const unsigned char *>(src) + o, len, barT);
-                }
-            }
-        } else {
-            for (uint32_t i = t; i < R * TILE; i += bd) sS[i] = src[i];
-        }
-    };
-    if constexpr (K::PREG) {
-        stage_one(gP);                                       // pass 1: Pinv, lifted into registers below
-    } else if (tma) {
+    if (tma) {
         if (t == 0) {
             constexpr uint32_t total = (uint32_t)(sizeof(T) * R * TILE);
             constexpr uint32_t CHB = 16384;
@@ -356,26 +314,13 @@ __device__ __forceinline__ uint32_t pcg_grid_body(const T *__restrict__ gS_all, 
     }
     if (tma) mbar_wait(barT, 0);
     __syncthreads();
-    T ms[K::SMALL ? W : 1], mp[(K::SMALL || K::PREG) ? W : 1];
-    if constexpr (K::PREG) {
-        // this thread's Pinv row -> registers (the two tiles the reference never reads are taken as zero), then pass 2: S
-        const T *rowP1 = sS + k * TILE + jn;
-#pragma unroll
-        for (uint32_t c = 0; c < W; ++c) {
-            const bool z = !is_row || (b == 0 && c < n) || (b == N - 1 && c >= 2 * n);
-            mp[c] = z ? T(0) : rowP1[c * n];
-        }
-        __syncthreads();
-        stage_one(gS);
-        if (tma) mbar_wait(barT, 1);
-        __syncthreads();
-    }
     if (cta == 0)
         for (uint32_t i = t; i < n * n; i += bd) { sS[i] = T(0); sP[i] = T(0); }
     if (cta == CTAS - 1)
         for (uint32_t i = t; i < n * n; i += bd) { sS[(R - 1) * TILE + 2 * n * n + i] = T(0); sP[(R - 1) * TILE + 2 * n * n + i] = T(0); }
     __syncthreads();
 
+    T ms[K::SMALL ? W : 1], mp[K::SMALL ? W : 1];
     const T *rowS = sS + k * TILE + jn, *rowP = sP + k * TILE + jn;
     if constexpr (K::SMALL) {
 #pragma unroll
@@ -392,7 +337,6 @@ __device__ __forceinline__ uint32_t pcg_grid_body(const T *__restrict__ gS_all, 
     };
     auto band_P = [&](const T *win) -> T {
         if constexpr (K::SMALL) return chain_padded<T, n, XS>(mp, win);
-        else if constexpr (K::PREG) return is_row ? chain_padded_mreg<n, XS>(mp, win) : T(0);
         else return is_row ? chain_padded_smem<T, n, XS>(rowP, win) : T(0);
     };
 

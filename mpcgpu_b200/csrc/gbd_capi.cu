@@ -153,7 +153,7 @@ std::vector<Variant> &variants()
         make_variant<float, 6, 12, 4, true>(),    make_variant<float, 6, 12, 1, true>(),
         make_variant<float, 6, 12, 2, false>(),
         make_variant<float, 2, 3, 1, true>(),     make_variant<float, 2, 3, 3, false>(),
-        make_grid<float, 64, 256, 2>(),           make_grid<float, 64, 256, 4>(),
+        make_grid<float, 64, 256, 2>(),
         make_grid<float, 14, 512, 4>(),           make_grid<float, 14, 128, 1>(),
         make_grid<float, 14, 32, 1>(),            make_grid<float, 14, 256, 2>(),
         make_grid<float, 6, 12, 1>(),             make_grid<float, 2, 3, 1>(),
