@@ -40,6 +40,8 @@ struct Variant {
     const void *kernel;
     bool prepared;
     size_t ws_words;   // grid kernel: u64 words of packet workspace
+    int resident = -1;       // cluster kernels: clusters of this shape the device can hold (set by prepare)
+    bool unusable = false;   // the device cannot place even one cluster of this size: defaults skip the variant
 };
 
 template <typename T, uint32_t n, uint32_t N, uint32_t C, bool REGS>
@@ -203,9 +205,10 @@ Variant *find_variant(uint32_t n, uint32_t N, bool f64, bool batched)
     Variant *first = nullptr, *first_b = nullptr;
     for (auto &v : variants()) {
         if (v.n != n || v.N != N || v.f64 != f64) continue;
+        if ((wantC || wantMode >= 0) && (wantC == 0 || v.C == wantC) && (wantMode < 0 || v.mode == wantMode)) return &v;
+        if (v.unusable) continue;
         if (!first) first = &v;
         if (!first_b && (v.mode == 3 || v.mode == 6 || v.mode == 8 || v.mode == 12)) first_b = &v;      // 2-CTA/SM build: the default for batched launches
-        if ((wantC || wantMode >= 0) && (wantC == 0 || v.C == wantC) && (wantMode < 0 || v.mode == wantMode)) return &v;
     }
     if (wantC || wantMode >= 0) return nullptr;
     if (batched) {
@@ -214,23 +217,13 @@ Variant *find_variant(uint32_t n, uint32_t N, bool f64, bool batched)
         for (auto &t : batched_defaults)
             if (t.n == n && t.N == N && t.f64 == f64)
                 for (auto &v : variants())
-                    if (v.n == n && v.N == N && v.f64 == f64 && v.C == t.C && v.mode == t.mode) return &v;
+                    if (v.n == n && v.N == N && v.f64 == f64 && v.C == t.C && v.mode == t.mode && !v.unusable) return &v;
     }
     return (batched && first_b) ? first_b : first;
 }
 
-int prepare(Variant &v)
-{
-    if (v.prepared) return GBD_PCG_OK;
-    std::lock_guard<std::mutex> lk(g_mu);
-    if (v.prepared) return GBD_PCG_OK;
-    if (v.smem > 48 * 1024) CK(cudaFuncSetAttribute(v.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem));
-    if (v.C > 8 && v.mode != 4) CK(cudaFuncSetAttribute(v.kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    v.prepared = true;
-    return GBD_PCG_OK;
-}
-
-// how many clusters of this variant the device can hold at once (persistent-grid size for batches)
+// how many clusters of this variant the device can hold at once (persistent-grid size for batches); 0 when the device
+// cannot place a cluster of this size at all (a 16-CTA cluster needs 16 free SMs inside one GPC)
 int max_clusters(Variant &v, int *out)
 {
     cudaLaunchConfig_t cfg = {};
@@ -242,9 +235,43 @@ int max_clusters(Variant &v, int *out)
     at[0].val.clusterDim.x = v.C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     int nc = 0;
-    CK(cudaOccupancyMaxActiveClusters(&nc, v.kernel, &cfg));
+    if (cudaOccupancyMaxActiveClusters(&nc, v.kernel, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        nc = 0;
+    }
     *out = nc;
     return GBD_PCG_OK;
+}
+
+int prepare(Variant &v)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (v.prepared) return GBD_PCG_OK;
+    if (v.smem > 48 * 1024) CK(cudaFuncSetAttribute(v.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem));
+    if (v.C > 8 && v.mode != 4) CK(cudaFuncSetAttribute(v.kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    if (v.mode != 4) {
+        // GBD_PCG_MAX_CLUSTER=c pretends the device cannot place clusters larger than c (tests of the fallback chain)
+        static const int cap = [] { const char *e = getenv("GBD_PCG_MAX_CLUSTER"); return e ? atoi(e) : 0; }();
+        max_clusters(v, &v.resident);
+        v.unusable = v.resident < 1 || (cap > 0 && (int)v.C > cap);
+    }
+    v.prepared = true;
+    return GBD_PCG_OK;
+}
+
+// the variant a launch will use: the tuned or default one, or -- when this device cannot place its cluster size -- the
+// next usable default for the shape (every variant computes the same bits, so only speed changes)
+Variant *resolve_variant(uint32_t n, uint32_t N, bool f64, bool batched, int *rc)
+{
+    *rc = GBD_PCG_ERR_UNSUPPORTED;
+    for (;;) {
+        Variant *v = find_variant(n, N, f64, batched);
+        if (!v) return nullptr;
+        const int r = prepare(*v);
+        if (r) { *rc = r; return nullptr; }
+        if (!v->unusable) { *rc = GBD_PCG_OK; return v; }
+        if (find_variant(n, N, f64, batched) == v) return nullptr;      // explicitly tuned to a shape this device cannot run
+    }
 }
 
 // grid kernel: one cooperative launch per system; packet workspace per (kernel, stream), zeroed once
@@ -300,25 +327,14 @@ int launch(uint32_t n, uint32_t N, uint32_t batch, const T *S, const T *P, const
            uint32_t *host_result = nullptr)
 {
     if (!S || !P || !g || !lam || !iters || !flag || batch == 0 || N < 2 || n == 0) return GBD_PCG_ERR_BADARG;
-    Variant *v = find_variant(n, N, sizeof(T) == 8, batch > 1);
-    if (!v) return GBD_PCG_ERR_UNSUPPORTED;
-    int rc = prepare(*v);
-    if (rc) return rc;
+    int rc;
+    Variant *v = resolve_variant(n, N, sizeof(T) == 8, batch > 1, &rc);
+    if (!v) return rc;
 
     if (v->mode == 4) return launch_grid<T>(*v, batch, S, P, g, lam, r, p, iters, flag, max_iter, tol, st, no_tma);
 
     uint32_t nclusters = batch;
-    if (batch > 1) {
-        static thread_local const void *cached_k = nullptr;
-        static thread_local int cached_nc = 0;
-        if (cached_k != v->kernel) {
-            int nc = 0;
-            rc = max_clusters(*v, &nc);
-            if (rc) return rc;
-            cached_k = v->kernel; cached_nc = nc > 0 ? nc : 1;
-        }
-        if (nclusters > (uint32_t)cached_nc) nclusters = (uint32_t)cached_nc;
-    }
+    if (batch > 1 && nclusters > (uint32_t)v->resident) nclusters = (uint32_t)v->resident;   // persistent clusters loop over the batch
     PcgArgs<T> a;
     a.S = S; a.Pinv = P; a.gamma = g; a.lambda = lam; a.r_out = r; a.p_out = p;
     a.iters = iters; a.max_iter_exit = flag; a.batch = batch; a.max_iter = max_iter; a.exit_tol = tol;
@@ -470,8 +486,10 @@ int gbd_pcg_linsys_f32(uint32_t n, uint32_t N, const float *d_S, const float *d_
     timespec t0, t1;
     CK(cudaDeviceSynchronize());
     clock_gettime(CLOCK_MONOTONIC, &t0);
-    Variant *v = find_variant(n, N, false, false);
-    const bool mirror = v && v->mode != 4;              // the cluster kernels write the two results into the mapped slots
+    int vrc;
+    Variant *v = resolve_variant(n, N, false, false, &vrc);
+    if (!v) return vrc;
+    const bool mirror = v->mode != 4;              // the cluster kernels write the two results into the mapped slots
     int rc = launch<float>(n, N, 1, d_S, d_Pinv, d_gamma, d_lambda, d_r, d_p, d_iters, d_max_iter_exit, max_iter,
                            exit_tol, (cudaStream_t)0, false, mirror ? pin_dev : nullptr);
     if (rc) return rc;

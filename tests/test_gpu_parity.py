@@ -159,6 +159,38 @@ def test_batched_uneven_iteration_counts(torch_cuda, capi, oracle_pcg):
     assert want["iters"].min() <= 5 and want["max_iter_exit"].any()      # from almost-converged to capped
 
 
+@pytest.mark.parametrize("cap", [8, 1])
+def test_fallback_when_cluster_size_cannot_be_placed(torch_cuda, capi, oracle_pcg, cap):
+    """A device that cannot place the default 16-CTA cluster (GBD_PCG_MAX_CLUSTER simulates it) falls back to the next
+    variant of the shape -- cap 1 leaves only the grid kernel -- with the same bits."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import numpy as np, torch, sys\n"
+        f"sys.path.insert(0, {root!r})\n"
+        "import mpcgpu_b200 as m\n"
+        "from mpcgpu_b200 import synth\n"
+        "d = synth.make_systems(14, 128, batch=1, seed=7)\n"
+        "S, P, g = (torch.from_numpy(d[k][0]).cuda() for k in ('S', 'Pinv', 'gamma'))\n"
+        "lam = torch.zeros(14 * 128, device='cuda')\n"
+        "it = torch.zeros(1, dtype=torch.int32, device='cuda'); fl = torch.zeros(1, dtype=torch.uint8, device='cuda')\n"
+        "m.pcg_launch(14, 128, S, P, g, lam, None, None, None, None, it, fl, 167, 1e-4)\n"
+        "torch.cuda.synchronize()\n"
+        "np.save(sys.argv[1], lam.cpu().numpy()); print(int(it.item()), int(fl.item()))\n")
+    out = os.path.join(root, "tests", "_build", f"fallback_{cap}.npy")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    env = dict(os.environ, GBD_PCG_MAX_CLUSTER=str(cap))
+    res = subprocess.run([sys.executable, "-c", code, out], capture_output=True, text=True, timeout=150, env=env)
+    assert res.returncode == 0, res.stderr[-2000:]
+    iters, flag = (int(x) for x in res.stdout.split()[-2:])
+    d = synth.make_systems(14, 128, batch=1, seed=7)
+    want = oracle_pcg.pcg(d["S"][0], d["Pinv"][0], d["gamma"][0], d["lambda0"][0], 14, 128, 167, 1e-4)
+    assert iters == want["iters"] and bool(flag) == want["max_iter_exit"]
+    assert np.array_equal(np.load(out), want["lam"])
+
+
 def test_full_size_batch_properties(torch_cuda, capi, oracle_pcg):
     """BASELINE config 4 size (1024 x N=128): too big for the oracle in seconds, so check
     size-independent properties: every system's fp64 residual is small, iteration counts equal the
