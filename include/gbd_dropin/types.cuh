@@ -9,24 +9,32 @@
 #include <cuda_runtime.h>
 #include "constants.cuh"
 
+// Sparse-matrix handle of the reference's QDLDL path; only the member names are contract.
 template <typename T>
 struct csr_t {
-    uint32_t *row_ptr;
-    uint32_t *col_ind;
+    uint32_t *row_ptr, *col_ind;
     T *val;
     uint32_t rows, cols, nnz;
 };
 
+// Solver settings.  Member names, their order and the positional constructor are contract (include/mpcsim.cuh:212-233
+// assigns pcg_block / pcg_exit_tol / pcg_max_iter by name); the defaults come from constants.cuh.
 template <typename T>
 struct pcg_config {
-    T pcg_exit_tol;
-    uint32_t pcg_max_iter;
-    dim3 pcg_grid;
-    dim3 pcg_block;
-    int empty_pinv;
-    pcg_config(T exit_tol = pcg_constants::DEFAULT_EPSILON<T>, uint32_t max_iter = pcg_constants::DEFAULT_MAX_PCG_ITER,
-               dim3 grid = pcg_constants::DEFAULT_GRID, dim3 block = pcg_constants::DEFAULT_BLOCK, int empty_pinv_ = 1)
-        : pcg_exit_tol(exit_tol), pcg_max_iter(max_iter), pcg_grid(grid), pcg_block(block), empty_pinv(empty_pinv_)
+    T pcg_exit_tol = pcg_constants::DEFAULT_EPSILON<T>;
+    uint32_t pcg_max_iter = pcg_constants::DEFAULT_MAX_PCG_ITER;
+    dim3 pcg_grid = pcg_constants::DEFAULT_GRID;
+    dim3 pcg_block = pcg_constants::DEFAULT_BLOCK;
+    int empty_pinv = 1;
+
+    pcg_config() = default;
+    pcg_config(T tol, uint32_t iters = pcg_constants::DEFAULT_MAX_PCG_ITER, dim3 grid = pcg_constants::DEFAULT_GRID,
+               dim3 block = pcg_constants::DEFAULT_BLOCK, int no_pinv = 1)
     {
+        pcg_exit_tol = tol;
+        pcg_max_iter = iters;
+        pcg_grid = grid;
+        pcg_block = block;
+        empty_pinv = no_pinv;
     }
 };
