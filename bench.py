@@ -171,16 +171,18 @@ def run_reference_arm(args):
     # one trajectory's solves are sequentially dependent and QDLDL is sequential: 1 thread is all this
     # workload can use.  Each "step" is a bounded sample of solves; K steps are timed.
     per_step_s = min(2.0, max(0.02, 60.0 / max(1, args.steps + args.warmup)))
+    # --gpus N: the GPU arm runs N independent trajectory streams (replicas), so this arm runs N streams too, one thread each
+    nth = max(1, min(int(args.gpus), os.cpu_count() or 1))
     vals = None
     from oracle import qdldl
     have_ref = qdldl.available()
     if have_ref:
         vals = qdldl.values(systems["S"], N_STATE, N_KNOT)
-        sec1, _ = qdldl.time_batched(vals, systems["gamma"], N_STATE, N_KNOT, reps=1, nthreads=1)
+        sec1, _ = qdldl.time_batched(vals, systems["gamma"], N_STATE, N_KNOT, reps=1, nthreads=nth)
         reps = max(1, int(per_step_s / sec1))
 
         def step():
-            s, _ = qdldl.time_batched(vals, systems["gamma"], N_STATE, N_KNOT, reps=reps, nthreads=1)
+            s, _ = qdldl.time_batched(vals, systems["gamma"], N_STATE, N_KNOT, reps=reps, nthreads=nth)
             return s, reps * 64
         kind = "reference"
     else:
@@ -193,6 +195,7 @@ def run_reference_arm(args):
                          N_KNOT, MAX_ITER, EXIT_TOL)
             return time.perf_counter() - t0, 8
         kind = "port"
+        nth = 1
     for _ in range(args.warmup):
         step()
     tot_s, tot_n = 0.0, 0
@@ -225,9 +228,10 @@ def run_reference_arm(args):
         "config": {"workload": "IIWA-size single trajectory: n=14, N=128, fp32 (BASELINE.json configs[1])",
                    "solver": "QDLDL factor+solve (include/qdldl/sqp.cuh:22-49)" if have_ref else "oracle PCG port",
                    "host_cores_available": ncores},
-        "cpu_baseline": {"value": value, "unit": "solves/s", "cores": 1, "kind": kind,
-                         "sample": f"{tot_n} solves in {args.steps} steps, 1 thread (one trajectory is sequential; "
-                                   f"QDLDL is single-threaded by design)"},
+        "cpu_baseline": {"value": value, "unit": "solves/s", "cores": nth, "kind": kind,
+                         "sample": f"{tot_n} solves in {args.steps} steps, {nth} thread(s): one per trajectory stream, as many "
+                                   f"streams as the GPU arm has replicas (one trajectory is sequential; QDLDL is "
+                                   f"single-threaded by design)"},
         "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
