@@ -17,6 +17,11 @@
  *
  * Results are bit-identical to the reference kernel pcg<T,n,N> (same floating-point operation
  * order: sequential FMA over the band row, GLASS halving trees for the dots, IEEE division).
+ *
+ * Process model: one CUDA device per process (the multi-GPU path is one process per GPU): kernel
+ * attributes and cluster occupancy are cached per kernel, not per device.  Entry points taking a stream
+ * may be called from several host threads on different streams; gbd_pcg_linsys_f32 brackets the legacy
+ * default stream like the reference's stopwatch window and is one caller at a time.
  */
 #ifndef GBD_PCG_H
 #define GBD_PCG_H
