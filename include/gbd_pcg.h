@@ -15,13 +15,23 @@
  *   gamma, lambda, r, p : [N*n]
  * Batched variants prepend a [batch] dimension to every array.
  *
- * Results are bit-identical to the reference kernel pcg<T,n,N> (same floating-point operation
- * order: sequential FMA over the band row, GLASS halving trees for the dots, IEEE division).
+ * Numerics (gbd_pcg_set_numerics): two kernel families solve the same problem behind the same entry points.
+ *   GBD_PCG_NUMERICS_FAST (default)  tolerance parity with the reference kernel pcg<T,n,N>: same algorithm, exit rule and
+ *       iteration-count meaning, but its own summation order and a single-reduction form of the CG recurrence
+ *       (include/gbd/gbd_cluster_pcg_fast.cuh).  Stated tolerance (tests/test_gpu_fast.py): iteration
+ *       count within +-2 of the reference kernel's, max_iter_exit identical unless within 2 of the cap,
+ *       max|lambda - lambda_ref| / max|lambda_ref| <= 1e-3, fp64 relative residual <= 1.1 x the reference kernel's.
+ *       Results are deterministic (no atomics: same input, same bits, whichever cluster solves a system).
+ *   GBD_PCG_NUMERICS_BITEXACT  bit-identical to the reference kernel (same floating-point operation order: sequential
+ *       FMA over the band row, GLASS halving trees for the dots, IEEE division); about 2x slower.
+ *   Shapes without a fast kernel (fp64, N = 512) are solved by the bit-exact family under either setting.
  *
  * Process model: one CUDA device per process (the multi-GPU path is one process per GPU): kernel
- * attributes and cluster occupancy are cached per kernel, not per device.  Entry points taking a stream
- * may be called from several host threads on different streams; gbd_pcg_linsys_f32 brackets the legacy
- * default stream like the reference's stopwatch window and is one caller at a time.
+ * attributes, cluster occupancy, work counters and packet workspaces are created once, for the device that
+ * is current at the first compute call; a compute call made with another device current returns
+ * GBD_PCG_ERR_DEVICE.  Entry points taking a stream may be called from several host threads on different
+ * streams; gbd_pcg_linsys_f32 brackets the legacy default stream like the reference's stopwatch window and
+ * is one caller at a time.
  */
 #ifndef GBD_PCG_H
 #define GBD_PCG_H
@@ -38,10 +48,11 @@ typedef enum gbd_pcg_status {
     GBD_PCG_ERR_UNSUPPORTED = -1, /* (n, N, dtype) has no compiled kernel; see gbd_pcg_supported() */
     GBD_PCG_ERR_BADARG = -2,      /* null pointer, N < 2, batch == 0, ... */
     GBD_PCG_ERR_CUDA = -3,        /* a CUDA call failed; code in gbd_pcg_last_cuda_error() */
-    GBD_PCG_ERR_NODEVICE = -4     /* no CUDA device / driver: there is NO CPU fallback */
+    GBD_PCG_ERR_NODEVICE = -4,    /* no CUDA device / driver: there is NO CPU fallback */
+    GBD_PCG_ERR_DEVICE = -5       /* the current CUDA device is not the one this process first used the library on */
 } gbd_pcg_status;
 
-#define GBD_PCG_ABI_VERSION 1
+#define GBD_PCG_ABI_VERSION 2
 
 int gbd_pcg_abi_version(void);
 const char *gbd_pcg_strerror(int status);
@@ -55,13 +66,28 @@ int gbd_pcg_num_variants(void);
 int gbd_pcg_variant_at(int i, uint32_t *n, uint32_t *N, uint32_t *cluster, int *mode, int *is_f64,
                        uint32_t *threads, size_t *smem_bytes);
 
+/* Kernel family used when no tuning is set: GBD_PCG_NUMERICS_FAST (default; environment GBD_PCG_NUMERICS=exact selects the
+ * other one at load time) or GBD_PCG_NUMERICS_BITEXACT.  Process-wide; takes effect for subsequent launches. */
+#define GBD_PCG_NUMERICS_BITEXACT 0
+#define GBD_PCG_NUMERICS_FAST 1
+int gbd_pcg_set_numerics(int numerics);
+int gbd_pcg_get_numerics(void);
+
+/* The variant a launch of this shape would run right now (tuning, numerics and what the device can place taken into
+ * account): cluster size (CTA count for the whole-GPU kernels), mode as in gbd_pcg_set_tuning, threads per CTA, dynamic
+ * shared memory, and the kernel's name as profilers print it (without template arguments).  Needs a CUDA device. */
+int gbd_pcg_resolved_variant(uint32_t n, uint32_t N, int is_f64, int batched, uint32_t *cluster, int *mode, uint32_t *threads,
+                             size_t *smem_bytes, char *kernel_name, size_t kernel_name_len);
+
 /* Tuning knob: pick the cluster size (CTAs per system) and kernel build used for (n, N).
  * mode: 0 = v1 kernel, tiles in shared memory; 1 = v1, tiles in registers; 2 = v2 kernel (st.async +
  * mbarrier signalling), 1 CTA/SM register budget; 3 = v2, 2 CTAs/SM budget; 4 = grid kernel (whole GPU on
  * one system, L2 packets); 5 = v3 kernel (two matrix rows per thread), 1 CTA/SM budget; 6 = v3, 2 CTAs/SM;
  * 7 = v4 kernel (self-validating {value, epoch} packets polled in shared memory), 1 CTA/SM; 8 = v4, 2 CTAs/SM;
- * 9, 10 = v4 A/B and timeline builds.
- * cluster = 0 and mode = -1 restore the built-in default.  All modes give bit-identical results. */
+ * 10, 14 = v4 / v2 timeline builds; 11, 12 = v5 kernel (v3's mapping + v4's packets).  Modes 0 .. 14 give bit-identical results.
+ * 20 = fast cluster kernel (tolerance parity, see Numerics above), 21 = its 2 CTAs/SM build, 22 = its timeline build,
+ * 24 = fast whole-GPU kernel, 26 = fast batched kernel.  A tuning overrides gbd_pcg_set_numerics for its shape.
+ * cluster = 0 and mode = -1 restore the built-in default. */
 int gbd_pcg_set_tuning(uint32_t n, uint32_t N, int is_f64, uint32_t cluster, int mode);
 
 /*
@@ -117,10 +143,14 @@ int gbd_pcg_solve_batched_f32(uint32_t n, uint32_t N, uint32_t batch, const floa
  * count and exit flag (the reference returns the constant 1, interface.cuh:88), and (c) keeps its
  * device buffers and stream in a reusable plan instead of cudaMalloc/cudaFree per call.
  * Host buffers may be pageable or pinned; `batch` systems are solved per call.
+ * Pinned / registered buffers are read and written in place by the kernel (zero-copy); the plan remembers the device alias
+ * of every such buffer it has seen.  A buffer that is unregistered or freed while the plan is alive must be forgotten with
+ * gbd_pcg_plan_invalidate before its address can be reused for another allocation.
  */
 typedef struct gbd_pcg_plan gbd_pcg_plan;
 int gbd_pcg_plan_create(uint32_t n, uint32_t N, uint32_t batch, int is_f64, gbd_pcg_plan **out);
 int gbd_pcg_plan_destroy(gbd_pcg_plan *plan);
+int gbd_pcg_plan_invalidate(gbd_pcg_plan *plan);   /* forget the cached device aliases of caller buffers */
 int gbd_pcg_plan_solve_host_f32(gbd_pcg_plan *plan, const float *h_S, const float *h_Pinv, const float *h_gamma,
                                 float *h_lambda, uint32_t max_iter, float exit_tol, uint32_t *h_iters,
                                 uint8_t *h_max_iter_exit);

@@ -8,7 +8,9 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libgbdpcg.so")
 
-OK, ERR_UNSUPPORTED, ERR_BADARG, ERR_CUDA, ERR_NODEVICE = 0, -1, -2, -3, -4
+OK, ERR_UNSUPPORTED, ERR_BADARG, ERR_CUDA, ERR_NODEVICE, ERR_DEVICE = 0, -1, -2, -3, -4, -5
+NUMERICS_BITEXACT, NUMERICS_FAST = 0, 1
+FAST_MODES = (20, 21, 22, 24, 26)      # tolerance-parity kernel families (include/gbd_pcg.h)
 
 # every symbol include/gbd_pcg.h declares (tests check the library exports all of them)
 SYMBOLS = [
@@ -20,7 +22,8 @@ SYMBOLS = [
     "gbd_compute_dz_f32", "gbd_step_plan_create", "gbd_step_plan_destroy", "gbd_step_run_f32", "gbd_step_results",
     "gbd_step_device_flags", "gbd_schur_csr_nnz", "gbd_schur_csr_pattern_i32", "gbd_schur_csr_values_f32",
     "gbd_bcr_supported", "gbd_bcr_solve_f32", "gbd_bcr_solve_batched_f32", "gbd_bcr_solve_flagged_f32",
-    "gbd_step_run_fallback_f32",
+    "gbd_step_run_fallback_f32", "gbd_pcg_set_numerics", "gbd_pcg_get_numerics", "gbd_pcg_resolved_variant",
+    "gbd_pcg_plan_invalidate",
 ]
 
 _lib = None
@@ -106,6 +109,14 @@ def lib():
     L.gbd_bcr_solve_flagged_f32.argtypes = [u32, u32, u32, vp, vp, vp, vp, vp]
     L.gbd_step_run_fallback_f32.restype = C.c_int
     L.gbd_step_run_fallback_f32.argtypes = [vp, vp, vp, vp, vp, f32, vp, vp, u32, f32, vp]
+    L.gbd_pcg_set_numerics.restype = C.c_int
+    L.gbd_pcg_set_numerics.argtypes = [C.c_int]
+    L.gbd_pcg_get_numerics.restype = C.c_int
+    L.gbd_pcg_resolved_variant.restype = C.c_int
+    L.gbd_pcg_resolved_variant.argtypes = [u32, u32, C.c_int, C.c_int, C.POINTER(u32), C.POINTER(C.c_int), C.POINTER(u32),
+                                           C.POINTER(C.c_size_t), C.c_char_p, C.c_size_t]
+    L.gbd_pcg_plan_invalidate.restype = C.c_int
+    L.gbd_pcg_plan_invalidate.argtypes = [vp]
     L.gbd_pcg_set_debug_buffer.restype = None
     L.gbd_pcg_set_debug_buffer.argtypes = [vp]
     _lib = L
@@ -126,5 +137,23 @@ def variants():
         check(L.gbd_pcg_variant_at(i, C.byref(n), C.byref(N), C.byref(c), C.byref(regs), C.byref(f64), C.byref(t),
                                    C.byref(smem)), "gbd_pcg_variant_at")
         out.append(dict(n=n.value, N=N.value, cluster=c.value, mode=regs.value, f64=bool(f64.value),
-                        threads=t.value, smem=smem.value))
+                        threads=t.value, smem=smem.value, fast=regs.value in FAST_MODES))
     return out
+
+
+def set_numerics(numerics: int):
+    """GBD_PCG_NUMERICS_FAST (tolerance parity, the default) or GBD_PCG_NUMERICS_BITEXACT; returns the previous setting."""
+    L = lib()
+    prev = L.gbd_pcg_get_numerics()
+    check(L.gbd_pcg_set_numerics(int(numerics)), "gbd_pcg_set_numerics")
+    return prev
+
+
+def resolved_variant(n: int, N: int, f64: bool = False, batched: bool = False):
+    """The kernel a launch of this shape would run now: dict(cluster, mode, threads, smem, kernel, fast)."""
+    c, t, mode, smem = C.c_uint32(), C.c_uint32(), C.c_int(), C.c_size_t()
+    name = C.create_string_buffer(96)
+    check(lib().gbd_pcg_resolved_variant(n, N, int(f64), int(batched), C.byref(c), C.byref(mode), C.byref(t), C.byref(smem),
+                                         name, 96), "gbd_pcg_resolved_variant")
+    return dict(cluster=c.value, mode=mode.value, threads=t.value, smem=smem.value, kernel=name.value.decode(),
+                fast=mode.value in FAST_MODES)

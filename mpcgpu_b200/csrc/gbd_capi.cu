@@ -7,171 +7,77 @@
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <map>
 #include <mutex>
 #include <vector>
 
 #include "../../include/gbd_pcg.h"
-#include "../../include/gbd/gbd_grid_pcg.cuh"
-#include "../../include/gbd/gbd_cluster_pcg_v3.cuh"
-#include "../../include/gbd/gbd_cluster_pcg_v4.cuh"
-#include "../../include/gbd/gbd_cluster_pcg_v5.cuh"
+#include "../../include/gbd/gbd_cluster_pcg.cuh"      // PcgArgs
+#include "../../include/gbd/gbd_grid_pcg.cuh"         // GridArgs
 #include "../../include/gbd/gbd_schur.cuh"
 #include "../../include/gbd/gbd_bcr.cuh"
-#include <map>
+#include "gbd_variants.h"
 
 namespace {
 
 using namespace gbd;
+using gbdlib::Variant;
+using gbdlib::mode_is_fast;
+using gbdlib::mode_is_grid;
 
-// mode: 0 = v1 kernel, tiles in shared memory; 1 = v1 kernel, tiles in registers;
-//       2 = v2 kernel (st.async/mbarrier signalling), 1 CTA/SM register budget; 3 = v2, 2 CTAs/SM budget;
-//       4 = grid kernel (whole GPU on one system, packets through L2; C then holds the CTA count)
-//       5 = v3 kernel (two matrix rows per thread, 8-lane knot rows), 1 CTA/SM register budget; 6 = v3, 2 CTAs/SM
-//       7 = v4 kernel (self-validating packets polled in shared memory, register N-way tree), 1 CTA/SM; 8 = v4, 2 CTAs/SM
-//      11 = v5 kernel (v3's two-rows-per-thread mapping + v4's packet exchange), 1 CTA/SM; 12 = v5, 2 CTAs/SM
-//      14 = v2 timeline build (same stamps as mode 10)
-//      10 = v4 timeline build: per-thread %clock stamps of iterations 8..11 into gbd_pcg_set_debug_buffer()
-struct Variant {
-    uint32_t n, N, C;
-    int mode;
-    bool f64;
-    uint32_t nt;
-    size_t smem;
-    const void *kernel;
-    bool prepared;
-    size_t ws_words;   // grid kernel: u64 words of packet workspace
-    int resident = -1;       // cluster kernels: clusters of this shape the device can hold (set by prepare)
-    bool unusable = false;   // the device cannot place even one cluster of this size: defaults skip the variant
-};
-
-template <typename T, uint32_t n, uint32_t N, uint32_t C, bool REGS>
-Variant make_variant()
-{
-    using K = ClusterPcg<T, n, N, C, REGS>;
-    return Variant{n, N, C, REGS ? 1 : 0, sizeof(T) == 8, K::NT, K::SMEM_BYTES,
-                   (const void *)pcg_cluster_kernel<T, n, N, C, REGS>, false, 0};
-}
-
-template <typename T, uint32_t n, uint32_t N, uint32_t C, uint32_t MINB>
-Variant make_v2()
-{
-    using K = ClusterPcg2<T, n, N, C>;
-    return Variant{n, N, C, MINB == 1 ? 2 : 3, sizeof(T) == 8, K::NT, K::SMEM_BYTES,
-                   (const void *)pcg_cluster_kernel_v2<T, n, N, C, MINB>, false, 0};
-}
-
-template <uint32_t n, uint32_t N, uint32_t C>
-Variant make_v2_prof()
-{
-    using K = ClusterPcg2<float, n, N, C>;
-    return Variant{n, N, C, 14, false, K::NT, K::SMEM_BYTES, (const void *)pcg_cluster_kernel_v2<float, n, N, C, 1, true>, false, 0};
-}
-
-template <uint32_t n, uint32_t N, uint32_t C, uint32_t MINB>
-Variant make_v3()
-{
-    using K = ClusterPcg3<n, N, C, true>;
-    return Variant{n, N, C, MINB == 1 ? 5 : 6, false, K::NT, K::SMEM_BYTES, (const void *)pcg_cluster_kernel_v3<n, N, C, MINB>, false, 0};
-}
-
-template <uint32_t n, uint32_t N, uint32_t C, uint32_t MINB, bool WEAK = false, bool PROF = false, uint32_t PER = 0>
-Variant make_v4()
-{
-    using K = ClusterPcg4<n, N, C, PER>;
-    return Variant{n, N, C, PROF ? 10 : (PER ? 9 : (MINB == 1 ? 7 : 8)), false, K::NT, K::SMEM_BYTES,
-                   (const void *)pcg_cluster_kernel_v4<n, N, C, MINB, WEAK, PROF, PER>, false, 0};
-}
-
-template <uint32_t n, uint32_t N, uint32_t C, uint32_t MINB>
-Variant make_v5()
-{
-    using K = ClusterPcg5<n, N, C, true>;
-    return Variant{n, N, C, MINB == 1 ? 11 : 12, false, K::NT, K::SMEM_BYTES, (const void *)pcg_cluster_kernel_v5<n, N, C, MINB>, false, 0};
-}
-
-template <typename T, uint32_t n, uint32_t N, uint32_t R>
-Variant make_grid()
-{
-    using K = GridPcg<T, n, N, R>;
-    return Variant{n, N, K::CTAS, 4, sizeof(T) == 8, K::NT_MIN < 128 ? 128 : K::NT_MIN, K::SMEM_BYTES,
-                   (const void *)pcg_grid_kernel<T, n, N, R>, false, K::WS_WORDS};
-}
-
-// (n, N) pairs: IIWA (n=14) at the reference's horizons (include/common/settings.cuh:123-138) plus
-// small systems for tests (n=2,N=3 is the GBD-PCG demo, GBD-PCG/examples/pcg_solve.cu:14-25).
-// The FIRST variant listed for an (n, N, dtype) is the default.
+// The table of compiled (n, N, cluster size, kernel family) variants, filled by the registrars of variants_*.cu.
 std::vector<Variant> &variants()
 {
-    static std::vector<Variant> v = {
-        // defaults first (measured on B200, profiles/r01c_ab_bench.json): v4 for single solves at N = 32 / 64,
-        // v2 at N = 128 / 256, v3 at N = 512; among the 2-CTA/SM builds (the batched default) v3 comes first
-        make_v4<14, 32, 4, 1>(),                  make_v4<14, 64, 8, 1>(),
-        make_v2<float, 14, 128, 16, 1>(),         make_v3<14, 128, 8, 2>(),
-        make_v2<float, 14, 128, 8, 2>(),
-        make_v2<float, 14, 128, 8, 1>(),          make_v2<float, 14, 128, 4, 1>(),
-        make_v2<float, 14, 32, 4, 1>(),           make_v3<14, 32, 1, 2>(),
-        make_v2<float, 14, 32, 8, 1>(),
-        make_v2<float, 14, 32, 2, 1>(),           make_v2<float, 14, 32, 4, 2>(),
-        make_v2<float, 14, 64, 8, 1>(),           make_v2<float, 14, 64, 4, 1>(),
-        make_v3<14, 64, 2, 2>(),
-        make_v2<float, 14, 256, 16, 1>(),         make_v2<float, 14, 256, 8, 1>(),
-        make_v3<14, 512, 16, 1>(),                make_v2<float, 14, 512, 16, 1>(),
-        make_v2<float, 14, 16, 4, 1>(),           make_v2<float, 14, 8, 8, 1>(),
-        make_v2<float, 6, 12, 4, 1>(),            make_v2<float, 6, 12, 1, 2>(),
-        make_v2<float, 2, 3, 1, 1>(),             make_v2<float, 2, 3, 3, 1>(),
-        make_v3<14, 128, 8, 1>(),
-        make_v3<14, 128, 16, 1>(),                make_v3<14, 128, 4, 1>(),
-        make_v3<14, 32, 2, 1>(),                  make_v3<14, 32, 4, 1>(),
-        make_v3<14, 32, 1, 1>(),                  make_v3<14, 32, 2, 2>(),
-        make_v3<14, 64, 4, 1>(),                  make_v3<14, 64, 8, 1>(),
-        make_v3<14, 64, 2, 1>(),
-        make_v3<14, 256, 16, 1>(),                make_v3<14, 256, 8, 1>(),
-        make_v3<14, 16, 2, 1>(),                  make_v3<14, 16, 1, 1>(),
-        make_v3<6, 12, 3, 1>(),
-        make_v4<14, 128, 16, 1>(),                make_v4<14, 128, 8, 1>(),
-        make_v4<14, 128, 8, 2>(),                 make_v4<14, 128, 16, 2>(),
-        make_v4<14, 32, 8, 1>(),
-        make_v4<14, 32, 2, 1>(),                  make_v4<14, 32, 4, 2>(),
-        make_v4<14, 64, 4, 1>(),
-        make_v4<14, 256, 16, 1>(),                make_v4<14, 256, 8, 1>(),
-        make_v4<14, 512, 16, 1>(),
-        make_v5<14, 128, 8, 1>(),                 make_v5<14, 128, 8, 2>(),
-        make_v5<14, 128, 4, 1>(),                 make_v5<14, 64, 4, 1>(),
-        make_v5<14, 64, 8, 1>(),                  make_v5<14, 32, 2, 1>(),
-        make_v5<14, 32, 4, 1>(),                  make_v5<14, 256, 8, 1>(),
-        make_v2_prof<14, 128, 16>(),              make_v2_prof<14, 128, 8>(),
-        make_v4<14, 128, 16, 1, false, true>(),   make_v4<14, 128, 8, 1, false, true>(),
-        make_v4<14, 32, 4, 1, false, true>(),     make_v4<14, 64, 8, 1, false, true>(),
-        make_variant<float, 14, 128, 8, true>(),  make_variant<float, 14, 128, 16, true>(),
-        make_variant<float, 14, 128, 4, true>(),  make_variant<float, 14, 128, 8, false>(),
-        make_variant<float, 14, 32, 4, true>(),   make_variant<float, 14, 32, 8, true>(),
-        make_variant<float, 14, 32, 2, true>(),   make_variant<float, 14, 32, 1, true>(),
-        make_variant<float, 14, 32, 8, false>(),
-        make_variant<float, 14, 64, 8, true>(),   make_variant<float, 14, 64, 4, true>(),
-        make_variant<float, 14, 256, 8, true>(),  make_variant<float, 14, 256, 16, true>(),
-        make_variant<float, 14, 512, 16, true>(), make_variant<float, 14, 512, 16, false>(),
-        make_variant<float, 14, 16, 4, true>(),   make_variant<float, 14, 8, 8, true>(),
-        make_variant<float, 14, 8, 2, true>(),
-        make_variant<float, 6, 12, 4, true>(),    make_variant<float, 6, 12, 1, true>(),
-        make_variant<float, 6, 12, 2, false>(),
-        make_variant<float, 2, 3, 1, true>(),     make_variant<float, 2, 3, 3, false>(),
-        make_grid<float, 64, 256, 2>(),
-        make_grid<float, 14, 512, 4>(),           make_grid<float, 14, 128, 1>(),
-        make_grid<float, 14, 32, 1>(),            make_grid<float, 14, 256, 2>(),
-        make_grid<float, 6, 12, 1>(),             make_grid<float, 2, 3, 1>(),
-        make_grid<double, 14, 32, 1>(),
-        make_variant<double, 14, 128, 8, false>(), make_variant<double, 14, 32, 8, false>(),
-        make_variant<double, 6, 12, 4, false>(),  make_variant<double, 2, 3, 1, false>(),
-    };
+    static std::vector<Variant> v = [] {
+        std::vector<Variant> t;
+        gbdlib::register_exact_v4(t);
+        gbdlib::register_exact_v1v2(t);
+        gbdlib::register_exact_v3v5(t);
+        gbdlib::register_fast(t);
+        gbdlib::register_grid(t);
+        return t;
+    }();
     return v;
 }
+
+// Measured defaults (B200; profiles/r01c_ab_bench.json for the bit-exact family, profiles/r02_* for the fast one): per
+// (n, N, numerics, single / batched) the preferred (cluster size, mode) in order; the first one the device can place is
+// used.  Shapes not listed take the first usable variant of the requested numerics in table order, then any usable variant
+// (a shape with no fast kernel is solved by the bit-exact one: stronger, never weaker).
+struct Pref { uint32_t n, N; bool fast, batched; uint32_t C; int mode; };
+const Pref g_prefs[] = {
+    // bit-exact, single solve
+    {14, 32, false, false, 4, 7},    {14, 64, false, false, 8, 7},    {14, 128, false, false, 16, 2},
+    {14, 128, false, false, 8, 2},   {14, 256, false, false, 16, 2},  {14, 256, false, false, 8, 2},
+    {14, 512, false, false, 16, 5},  {14, 512, false, false, 16, 2},
+    // bit-exact, batched
+    {14, 128, false, true, 4, 11},   {14, 32, false, true, 2, 11},    {14, 64, false, true, 2, 6},
+    {14, 128, false, true, 8, 6},    {14, 32, false, true, 1, 6},
+    // tolerance parity, single solve
+    {14, 128, true, false, 16, 20},  {14, 128, true, false, 8, 20},   {14, 32, true, false, 4, 20},
+    {14, 64, true, false, 8, 20},    {14, 256, true, false, 16, 20},
+    // tolerance parity, batched
+    {14, 128, true, true, 8, 20},    {14, 32, true, true, 2, 20},     {14, 64, true, true, 4, 20},
+};
 
 struct Tuning { uint32_t n, N; bool f64; uint32_t C; int mode; };
 std::vector<Tuning> &tunings() { static std::vector<Tuning> t; return t; }
 std::mutex g_mu;
 std::atomic<uint64_t> g_launches{0};
-uint32_t *g_dbg = nullptr;   // timeline builds (mode 10) write %clock stamps here
+std::atomic<int> g_numerics{-1};   // -1: not chosen yet (environment, else fast)
+uint32_t *g_dbg = nullptr;   // timeline builds write %clock stamps here
 thread_local int tl_cuda_err = 0;
+
+int numerics()
+{
+    int m = g_numerics.load(std::memory_order_relaxed);
+    if (m < 0) {
+        const char *e = getenv("GBD_PCG_NUMERICS");
+        m = (e && (!strcmp(e, "exact") || !strcmp(e, "bitexact") || !strcmp(e, "0"))) ? GBD_PCG_NUMERICS_BITEXACT : GBD_PCG_NUMERICS_FAST;
+        g_numerics.store(m, std::memory_order_relaxed);
+    }
+    return m;
+}
 
 int cuda_fail(cudaError_t e)
 {
@@ -182,8 +88,21 @@ int cuda_fail(cudaError_t e)
 }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(e_); } while (0)
 
+// One CUDA device per process (gbd_pcg.h): kernel attributes, cluster occupancy, work counters, packet workspaces and the
+// pinned result mirror are created once and belong to the device that was current at the first compute call.  A call made
+// with another device current would launch unprepared kernels on foreign buffers, so it is refused instead.
+int g_device = -1;
+int check_device()
+{
+    int dev = -1;
+    CK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_device < 0) g_device = dev;
+    return dev == g_device ? GBD_PCG_OK : GBD_PCG_ERR_DEVICE;
+}
+
 // Wait for a stream by polling it: the wake-up latency of cudaStreamSynchronize is several microseconds, which is a few
-// per cent of a 140 us solve.  Solves that run long fall back to the blocking wait so a core is not burnt for nothing.
+// per cent of a 100 us solve.  Solves that run long fall back to the blocking wait so a core is not burnt for nothing.
 cudaError_t spin_sync(cudaStream_t st)
 {
     timespec a, b;
@@ -198,28 +117,39 @@ cudaError_t spin_sync(cudaStream_t st)
     }
 }
 
+Variant *lookup(uint32_t n, uint32_t N, bool f64, uint32_t C, int mode)
+{
+    for (auto &v : variants())
+        if (v.n == n && v.N == N && v.f64 == f64 && (C == 0 || v.C == C) && (mode < 0 || v.mode == mode)) return &v;
+    return nullptr;
+}
+
 Variant *find_variant(uint32_t n, uint32_t N, bool f64, bool batched)
 {
-    uint32_t wantC = 0; int wantMode = -1;
-    for (auto &t : tunings()) if (t.n == n && t.N == N && t.f64 == f64) { wantC = t.C; wantMode = t.mode; }
-    Variant *first = nullptr, *first_b = nullptr;
-    for (auto &v : variants()) {
-        if (v.n != n || v.N != N || v.f64 != f64) continue;
-        if ((wantC || wantMode >= 0) && (wantC == 0 || v.C == wantC) && (wantMode < 0 || v.mode == wantMode)) return &v;
-        if (v.unusable) continue;
-        if (!first) first = &v;
-        if (!first_b && (v.mode == 3 || v.mode == 6 || v.mode == 8 || v.mode == 12)) first_b = &v;      // 2-CTA/SM build: the default for batched launches
+    {
+        uint32_t wantC = 0; int wantMode = -1;
+        for (auto &t : tunings()) if (t.n == n && t.N == N && t.f64 == f64) { wantC = t.C; wantMode = t.mode; }
+        if (wantC || wantMode >= 0) return lookup(n, N, f64, wantC, wantMode);
     }
-    if (wantC || wantMode >= 0) return nullptr;
-    if (batched) {
-        // measured batched defaults (profiles/r01c_ab_bench.json): v5 with 4 CTAs per system at N = 128, 2 at N = 32
-        static const Tuning batched_defaults[] = {{14, 128, false, 4, 11}, {14, 32, false, 2, 11}};
-        for (auto &t : batched_defaults)
-            if (t.n == n && t.N == N && t.f64 == f64)
-                for (auto &v : variants())
-                    if (v.n == n && v.N == N && v.f64 == f64 && v.C == t.C && v.mode == t.mode && !v.unusable) return &v;
+    const bool fast = !f64 && numerics() == GBD_PCG_NUMERICS_FAST;
+    for (int pass = fast ? 0 : 1; pass < 2; ++pass) {        // pass 0: fast kernels, pass 1: bit-exact kernels
+        const bool want_fast = pass == 0;
+        if (!f64)
+            for (const Pref &p : g_prefs)
+                if (p.n == n && p.N == N && p.fast == want_fast && p.batched == batched) {
+                    Variant *v = lookup(n, N, false, p.C, p.mode);
+                    if (v && !v->unusable) return v;
+                }
+        Variant *grid = nullptr;
+        for (auto &v : variants()) {
+            if (v.n != n || v.N != N || v.f64 != f64 || v.unusable || mode_is_fast(v.mode) != want_fast) continue;
+            if (v.mode == 10 || v.mode == 14 || v.mode == gbdlib::MODE_FAST_PROF) continue;      // timeline builds are never a default
+            if (mode_is_grid(v.mode)) { if (!grid) grid = &v; continue; }                          // whole-GPU kernels last
+            return &v;
+        }
+        if (grid) return grid;
     }
-    return (batched && first_b) ? first_b : first;
+    return nullptr;
 }
 
 // how many clusters of this variant the device can hold at once (persistent-grid size for batches); 0 when the device
@@ -248,8 +178,8 @@ int prepare(Variant &v)
     std::lock_guard<std::mutex> lk(g_mu);
     if (v.prepared) return GBD_PCG_OK;
     if (v.smem > 48 * 1024) CK(cudaFuncSetAttribute(v.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem));
-    if (v.C > 8 && v.mode != 4) CK(cudaFuncSetAttribute(v.kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    if (v.mode != 4) {
+    if (v.C > 8 && !mode_is_grid(v.mode)) CK(cudaFuncSetAttribute(v.kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    if (!mode_is_grid(v.mode)) {
         // GBD_PCG_MAX_CLUSTER=c pretends the device cannot place clusters larger than c (tests of the fallback chain)
         static const int cap = [] { const char *e = getenv("GBD_PCG_MAX_CLUSTER"); return e ? atoi(e) : 0; }();
         max_clusters(v, &v.resident);
@@ -303,8 +233,11 @@ int launch_grid(Variant &v, uint32_t batch, const T *S, const T *P, const T *g, 
         ga.a.iters = iters + i; ga.a.max_iter_exit = flag + i; ga.a.batch = 1; ga.a.max_iter = max_iter; ga.a.exit_tol = tol;
         ga.a.use_tma = (!no_tma && (((uintptr_t)ga.a.S | (uintptr_t)ga.a.Pinv) & 15u) == 0) ? 1u : 0u;
         ga.ws = w->ws;
-        ga.epoch_base = w->epoch;
-        w->epoch += 2u * max_iter + 4u;                      // upper bound on the phases one launch can use
+        {
+            std::lock_guard<std::mutex> lk(g_mu);
+            ga.epoch_base = w->epoch;
+            w->epoch += 2u * max_iter + 4u;                  // upper bound on the phases one launch can use
+        }
         cudaLaunchConfig_t cfg = {};
         cudaLaunchAttribute at[1];
         cfg.gridDim = dim3(v.C);
@@ -327,11 +260,13 @@ int launch(uint32_t n, uint32_t N, uint32_t batch, const T *S, const T *P, const
            uint32_t *host_result = nullptr)
 {
     if (!S || !P || !g || !lam || !iters || !flag || batch == 0 || N < 2 || n == 0) return GBD_PCG_ERR_BADARG;
-    int rc;
+    if (!lookup(n, N, sizeof(T) == 8, 0, -1)) return GBD_PCG_ERR_UNSUPPORTED;
+    int rc = check_device();
+    if (rc) return rc;
     Variant *v = resolve_variant(n, N, sizeof(T) == 8, batch > 1, &rc);
     if (!v) return rc;
 
-    if (v->mode == 4) return launch_grid<T>(*v, batch, S, P, g, lam, r, p, iters, flag, max_iter, tol, st, no_tma);
+    if (mode_is_grid(v->mode)) return launch_grid<T>(*v, batch, S, P, g, lam, r, p, iters, flag, max_iter, tol, st, no_tma);
 
     uint32_t nclusters = batch;
     if (batch > 1 && nclusters > (uint32_t)v->resident) nclusters = (uint32_t)v->resident;   // persistent clusters loop over the batch
@@ -345,18 +280,24 @@ int launch(uint32_t n, uint32_t N, uint32_t batch, const T *S, const T *P, const
         // v5 with more systems than resident clusters: clusters draw their next system from a counter (zeroed on this
         // stream ahead of the launch) -- GBD_PCG_STATIC_BATCH=1 keeps the fixed stride (A/B)
         static const bool static_batch = [] { const char *e = getenv("GBD_PCG_STATIC_BATCH"); return e && atoi(e) != 0; }();
-        if ((v->mode == 11 || v->mode == 12) && batch > nclusters && !static_batch) {
-            constexpr uint32_t SLOTS = 256;                  // launches in flight at once before a slot is reused
-            static uint32_t *counters = nullptr;
-            static uint32_t next_slot = 0;
-            uint32_t slot;
+        const bool draws = v->mode == 11 || v->mode == 12 || mode_is_fast(v->mode);
+        if (draws && batch > nclusters && !static_batch) {
+            // one counter per stream: the memset and the kernel that draws from it are stream-ordered, so the next launch on
+            // the same stream cannot zero the counter under a kernel that is still running, however many launches are queued
+            static std::map<cudaStream_t, uint32_t *> counters;
+            uint32_t *ctr;
             {
                 std::lock_guard<std::mutex> lk(g_mu);
-                if (!counters) CK(cudaMalloc((void **)&counters, SLOTS * sizeof(uint32_t)));
-                slot = next_slot++ % SLOTS;
+                auto it = counters.find(st);
+                if (it == counters.end()) {
+                    uint32_t *c = nullptr;
+                    CK(cudaMalloc((void **)&c, sizeof(uint32_t)));
+                    it = counters.emplace(st, c).first;
+                }
+                ctr = it->second;
             }
-            CK(cudaMemsetAsync(counters + slot, 0, sizeof(uint32_t), st));
-            a.work_counter = counters + slot;
+            CK(cudaMemsetAsync(ctr, 0, sizeof(uint32_t), st));
+            a.work_counter = ctr;
         }
     }
 
@@ -406,6 +347,7 @@ const char *gbd_pcg_strerror(int s)
         case GBD_PCG_ERR_BADARG: return "bad argument";
         case GBD_PCG_ERR_CUDA: return "CUDA error (see gbd_pcg_last_cuda_error)";
         case GBD_PCG_ERR_NODEVICE: return "no CUDA device (this library has no CPU fallback)";
+        case GBD_PCG_ERR_DEVICE: return "the current CUDA device is not the one this process first used the library on";
         default: return "unknown status";
     }
 }
@@ -432,6 +374,30 @@ int gbd_pcg_variant_at(int i, uint32_t *n, uint32_t *N, uint32_t *cluster, int *
     if (is_f64) *is_f64 = v.f64;
     if (threads) *threads = v.nt;
     if (smem_bytes) *smem_bytes = v.smem;
+    return GBD_PCG_OK;
+}
+
+int gbd_pcg_set_numerics(int m)
+{
+    if (m != GBD_PCG_NUMERICS_BITEXACT && m != GBD_PCG_NUMERICS_FAST) return GBD_PCG_ERR_BADARG;
+    g_numerics.store(m, std::memory_order_relaxed);
+    return GBD_PCG_OK;
+}
+
+int gbd_pcg_get_numerics(void) { return numerics(); }
+
+int gbd_pcg_resolved_variant(uint32_t n, uint32_t N, int is_f64, int batched, uint32_t *cluster, int *mode, uint32_t *threads,
+                             size_t *smem_bytes, char *kernel_name, size_t kernel_name_len)
+{
+    int rc = check_device();
+    if (rc) return rc;
+    Variant *v = resolve_variant(n, N, is_f64 != 0, batched != 0, &rc);
+    if (!v) return rc;
+    if (cluster) *cluster = v->C;
+    if (mode) *mode = v->mode;
+    if (threads) *threads = v->nt;
+    if (smem_bytes) *smem_bytes = v->smem;
+    if (kernel_name && kernel_name_len) snprintf(kernel_name, kernel_name_len, "%s", v->name);
     return GBD_PCG_OK;
 }
 
@@ -472,6 +438,7 @@ int gbd_pcg_linsys_f32(uint32_t n, uint32_t N, const float *d_S, const float *d_
                        double *elapsed_us)
 {
     if (!h_iters || !h_max_iter_exit) return GBD_PCG_ERR_BADARG;
+    { const int drc = check_device(); if (drc) return drc; }
     // same observable window as include/pcg/sqp.cuh:224-241 (device idle before, both results on the host and the device
     // idle after), but the two blocking cudaMemcpy + cudaDeviceSynchronize become two async copies into pinned slots and
     // one spin on the stream: ~15 us less host-side latency per SQP iteration
@@ -489,7 +456,7 @@ int gbd_pcg_linsys_f32(uint32_t n, uint32_t N, const float *d_S, const float *d_
     int vrc;
     Variant *v = resolve_variant(n, N, false, false, &vrc);
     if (!v) return vrc;
-    const bool mirror = v->mode != 4;              // the cluster kernels write the two results into the mapped slots
+    const bool mirror = !mode_is_grid(v->mode);              // the cluster kernels write the two results into the mapped slots
     int rc = launch<float>(n, N, 1, d_S, d_Pinv, d_gamma, d_lambda, d_r, d_p, d_iters, d_max_iter_exit, max_iter,
                            exit_tol, (cudaStream_t)0, false, mirror ? pin_dev : nullptr);
     if (rc) return rc;
@@ -517,6 +484,7 @@ int gbd_pcg_plan_create(uint32_t n, uint32_t N, uint32_t batch, int is_f64, gbd_
 {
     if (!out || batch == 0) return GBD_PCG_ERR_BADARG;
     if (!gbd_pcg_supported(n, N, is_f64)) return GBD_PCG_ERR_UNSUPPORTED;
+    { const int drc = check_device(); if (drc) return drc; }
     gbd_pcg_plan *p = (gbd_pcg_plan *)calloc(1, sizeof(gbd_pcg_plan));
     p->n = n; p->N = N; p->batch = batch; p->f64 = is_f64 != 0; p->esz = is_f64 ? 8 : 4;
     const size_t mat = (size_t)3 * n * n * N * batch * p->esz, vec = (size_t)n * N * batch * p->esz;
@@ -534,6 +502,13 @@ int gbd_pcg_plan_create(uint32_t n, uint32_t N, uint32_t batch, int is_f64, gbd_
         return cuda_fail(e);
     }
     *out = p;
+    return GBD_PCG_OK;
+}
+
+int gbd_pcg_plan_invalidate(gbd_pcg_plan *p)
+{
+    if (!p) return GBD_PCG_ERR_BADARG;
+    memset(p->alias, 0, sizeof(p->alias));
     return GBD_PCG_OK;
 }
 
@@ -635,6 +610,7 @@ int schur_launch(uint32_t N, uint32_t batch, float *G, const float *C, const flo
                  float rho, cudaStream_t st)
 {
     using K = gbd::SchurShape<n, m>;
+    { const int drc = check_device(); if (drc) return drc; }
     gbd::schur_phase1_kernel<n, m><<<dim3(N, batch), K::NT, K::P1_FLOATS * sizeof(float), st>>>(N, G, C, g, c, S, P, gam, rho);
     {   // phase 2 with programmatic stream serialization: its launch overlaps phase 1, griddepcontrol.wait orders the data
         cudaLaunchConfig_t cfg = {};
@@ -657,6 +633,7 @@ int schur_launch(uint32_t N, uint32_t batch, float *G, const float *C, const flo
 template <uint32_t n, uint32_t m>
 int dz_launch(uint32_t N, uint32_t batch, const float *Gi, const float *C, const float *g, const float *lam, float *dz, cudaStream_t st)
 {
+    { const int drc = check_device(); if (drc) return drc; }
     gbd::compute_dz_kernel<n, m><<<dim3(N, batch), 64, 0, st>>>(N, Gi, C, g, lam, dz);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e);
@@ -716,6 +693,7 @@ int gbd_step_plan_create(uint32_t n, uint32_t m, uint32_t N, uint32_t batch, gbd
 {
     if (!out || batch == 0 || N < 2) return GBD_PCG_ERR_BADARG;
     if (!gbd_schur_supported(n, m) || !gbd_pcg_supported(n, N, 0)) return GBD_PCG_ERR_UNSUPPORTED;
+    { const int drc = check_device(); if (drc) return drc; }
     gbd_step_plan *p = (gbd_step_plan *)calloc(1, sizeof(gbd_step_plan));
     p->n = n; p->m = m; p->N = N; p->batch = batch;
     const size_t mat = (size_t)3 * n * n * N * batch * sizeof(float), vec = (size_t)n * N * batch * sizeof(float);
@@ -765,8 +743,12 @@ static int step_run(gbd_step_plan *p, float *d_G, const float *d_C, const float 
                     float *d_lambda, float *d_dz, uint32_t max_iter, float exit_tol, void *stream, bool direct_fallback)
 {
     if (!p || !d_G || !d_C || !d_g || !d_c || !d_lambda || !d_dz) return GBD_PCG_ERR_BADARG;
+    // nothing is enqueued unless every stage of the step exists for this shape (d_G and d_lambda are overwritten by it)
+    if (direct_fallback && !gbd_bcr_supported(p->n, p->N)) return GBD_PCG_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = GBD_PCG_ERR_UNSUPPORTED;
+    int rc = check_device();
+    if (rc) return rc;
+    rc = GBD_PCG_ERR_UNSUPPORTED;
 #define X(a, b) if (p->n == a && p->m == b) rc = schur_launch<a, b>(p->N, p->batch, d_G, d_C, d_g, d_c, p->dS, p->dP, p->dgam, rho, st);
     GBD_SCHUR_SHAPES(X)
 #undef X
@@ -812,6 +794,7 @@ int bcr_launch(uint32_t batch, const float *S, const float *g, float *lam, cudaS
     auto kern = gbd::bcr_cluster_kernel<n, N, C, MINB, PROF>;
     static bool prepared = false;
     static int max_clusters = 0;
+    { const int drc = check_device(); if (drc) return drc; }
     {
         std::lock_guard<std::mutex> lk(g_mu);
         if (!prepared) {

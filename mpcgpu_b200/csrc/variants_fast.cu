@@ -1,0 +1,27 @@
+// variants_fast.cu -- tolerance-parity family (include/gbd/gbd_cluster_pcg_fast.cuh).
+#include "gbd_variants.h"
+#include "../../include/gbd/gbd_cluster_pcg_fast.cuh"
+
+namespace gbdlib {
+using namespace gbd;
+
+template <uint32_t n, uint32_t N, uint32_t C, uint32_t MINB, bool PROF = false>
+static Variant make_fast()
+{
+    using K = ClusterPcgFast<n, N, C>;
+    return Variant{n, N, C, PROF ? MODE_FAST_PROF : (MINB == 1 ? MODE_FAST : MODE_FAST2), false, K::NT, K::SMEM_BYTES,
+                   (const void *)pcg_cluster_kernel_fast<n, N, C, MINB, PROF>, "gbd::pcg_cluster_kernel_fast"};
+}
+
+void register_fast(std::vector<Variant> &v)
+{
+    const Variant list[] = {
+        make_fast<14, 128, 16, 1>(),  make_fast<14, 128, 8, 1>(),   make_fast<14, 32, 4, 1>(),
+        make_fast<14, 32, 2, 1>(),    make_fast<14, 64, 8, 1>(),    make_fast<14, 64, 4, 1>(),
+        make_fast<14, 256, 16, 1>(),  make_fast<14, 16, 4, 1>(),    make_fast<14, 8, 2, 1>(),
+        make_fast<6, 12, 3, 1>(),     make_fast<6, 12, 2, 1>(),     make_fast<2, 3, 1, 1>(),
+        make_fast<14, 128, 16, 1, true>(), make_fast<14, 128, 8, 1, true>(), make_fast<14, 32, 4, 1, true>(),
+    };
+    for (const Variant &x : list) v.push_back(x);
+}
+}  // namespace gbdlib

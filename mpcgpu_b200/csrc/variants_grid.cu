@@ -1,0 +1,27 @@
+// variants_grid.cu -- the whole GPU on one system (n = 64, N = 256 and the fallback behind every shape): packets through L2.
+#include "gbd_variants.h"
+#include "../../include/gbd/gbd_grid_pcg.cuh"
+
+namespace gbdlib {
+using namespace gbd;
+
+template <typename T, uint32_t n, uint32_t N, uint32_t R>
+static Variant make_grid()
+{
+    using K = GridPcg<T, n, N, R>;
+    Variant v{n, N, K::CTAS, MODE_GRID, sizeof(T) == 8, K::NT_MIN < 128 ? 128 : K::NT_MIN, K::SMEM_BYTES,
+              (const void *)pcg_grid_kernel<T, n, N, R>, "gbd::pcg_grid_kernel"};
+    v.ws_words = K::WS_WORDS;
+    return v;
+}
+
+void register_grid(std::vector<Variant> &v)
+{
+    const Variant list[] = {
+        make_grid<float, 64, 256, 2>(), make_grid<float, 14, 512, 4>(), make_grid<float, 14, 128, 1>(),
+        make_grid<float, 14, 32, 1>(),  make_grid<float, 14, 256, 2>(), make_grid<float, 6, 12, 1>(),
+        make_grid<float, 2, 3, 1>(),    make_grid<double, 14, 32, 1>(),
+    };
+    for (const Variant &x : list) v.push_back(x);
+}
+}  // namespace gbdlib

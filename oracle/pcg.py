@@ -104,6 +104,44 @@ def pcg(S, Pinv, gamma, lambda0, n: int, N: int, max_iter: int, exit_tol: float,
     return dict(lam=lam, iters=int(iters.value), max_iter_exit=bool(flag.value), r=r, p=p, eta=float(eta.value))
 
 
+_FAST_PATH = os.path.join(_HERE, "_build", "libpcg_fast_oracle.so")
+_fast = None
+
+
+def fast_lib():
+    """pcg_fast_oracle.c: the tolerance-parity kernels' own operation order, restated on the CPU."""
+    global _fast
+    if _fast is None:
+        src = os.path.join(_HERE, "pcg_fast_oracle.c")
+        if not os.path.exists(_FAST_PATH) or os.path.getmtime(_FAST_PATH) < os.path.getmtime(src):
+            subprocess.check_call(["make", "-s", "-C", _HERE, "oracle"])
+        _fast = C.CDLL(_FAST_PATH)
+        f32p = C.POINTER(C.c_float)
+        _fast.pcg_fast_oracle_f32.restype = C.c_int
+        _fast.pcg_fast_oracle_f32.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, f32p, f32p, f32p, f32p, C.c_uint32, C.c_float,
+                                              C.POINTER(C.c_uint32), C.POINTER(C.c_uint8), f32p, f32p, f32p]
+    return _fast
+
+
+def pcg_fast(S, Pinv, gamma, lambda0, n: int, N: int, cluster: int, max_iter: int, exit_tol: float):
+    """The fast kernels' arithmetic (Chronopoulos-Gear recurrence, per-CTA reductions for a cluster of `cluster` CTAs),
+    include/gbd/gbd_cluster_pcg_fast.cuh.  Same return dict as pcg()."""
+    S = np.ascontiguousarray(S, np.float32).reshape(-1)
+    Pinv = np.ascontiguousarray(Pinv, np.float32).reshape(-1)
+    gamma = np.ascontiguousarray(gamma, np.float32).reshape(-1)
+    lam = np.ascontiguousarray(lambda0, np.float32).reshape(-1).copy()
+    assert S.size == 3 * n * n * N and Pinv.size == S.size and gamma.size == n * N and lam.size == n * N
+    r = np.empty(n * N, np.float32)
+    p = np.empty(n * N, np.float32)
+    iters, flag, eta = C.c_uint32(0), C.c_uint8(0), C.c_float(0)
+    rc = fast_lib().pcg_fast_oracle_f32(n, N, cluster, _p(S, C.c_float), _p(Pinv, C.c_float), _p(gamma, C.c_float),
+                                        _p(lam, C.c_float), max_iter, exit_tol, C.byref(iters), C.byref(flag),
+                                        _p(r, C.c_float), _p(p, C.c_float), C.byref(eta))
+    if rc:
+        raise ValueError(f"pcg_fast_oracle rc={rc}")
+    return dict(lam=lam, iters=int(iters.value), max_iter_exit=bool(flag.value), r=r, p=p, eta=float(eta.value))
+
+
 def pcg_batched(S, Pinv, gamma, lambda0, n, N, batch, max_iter, exit_tol, contract=True):
     S = np.ascontiguousarray(S, np.float32).reshape(-1)
     Pinv = np.ascontiguousarray(Pinv, np.float32).reshape(-1)

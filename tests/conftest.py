@@ -10,6 +10,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "fast_numerics: GPU test that runs the tolerance-parity kernels (the library default)")
 
 
 @pytest.fixture(scope="session")
@@ -18,6 +19,23 @@ def capi():
     from mpcgpu_b200 import build, _capi
     build.build_lib()
     return _capi
+
+
+@pytest.fixture(autouse=True)
+def _numerics_for_module(request):
+    """The library defaults to the tolerance-parity (fast) kernels.  Every GPU test module written against bit-exactness
+    runs with GBD_PCG_NUMERICS_BITEXACT; tests/test_gpu_fast.py (and tests marked `fast_numerics`) run with the default."""
+    if request.node.get_closest_marker("gpu") is None:
+        yield
+        return
+    from mpcgpu_b200 import build, _capi
+    build.build_lib()
+    fast = request.node.get_closest_marker("fast_numerics") is not None
+    prev = _capi.set_numerics(_capi.NUMERICS_FAST if fast else _capi.NUMERICS_BITEXACT)
+    try:
+        yield
+    finally:
+        _capi.set_numerics(prev)
 
 
 @pytest.fixture(scope="session")

@@ -1,0 +1,46 @@
+"""CPU tests of oracle/pcg_fast_oracle.c, the restatement of the tolerance-parity kernels' operation order: on the
+reference's own IIWA systems it must agree with the reference kernel's stored answers (tests/golden, minted on a B200 by
+tools/make_golden.py) within the stated tolerance of SURVEY.md 8(c)(ii) for every cluster shape the kernels use."""
+import os
+
+import numpy as np
+import pytest
+
+from test_golden import GOLDEN, load
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_fast_order_within_tolerance_of_reference_kernel(oracle_pcg, path):
+    g = load(path)
+    n, N = g["n"], g["N"]
+    for run in g["runs"]:
+        r_ref = oracle_pcg.rel_residual(g["S"], g["gamma"], run["lam"], n, N)
+        for C in (4, 8, 16):
+            if N // C < 2:
+                continue
+            f = oracle_pcg.pcg_fast(g["S"], g["Pinv"], g["gamma"], np.zeros(n * N, np.float32), n, N, C, run["cap"], run["tol"])
+            assert abs(f["iters"] - run["iters"]) <= 2
+            if run["iters"] < run["cap"] - 2 or run["max_iter_exit"]:
+                assert f["max_iter_exit"] == run["max_iter_exit"]
+            assert np.abs(f["lam"].astype(np.float64) - run["lam"]).max() / np.abs(run["lam"]).max() <= 1e-3
+            assert oracle_pcg.rel_residual(g["S"], g["gamma"], f["lam"], n, N) <= 1.1 * r_ref + 1e-6
+
+
+def test_fast_order_solves_the_demo_system(oracle_pcg, g1):
+    """GBD-PCG/examples/pcg_solve.cu:14-25 (n = 2, N = 3) against the fp64 direct solution."""
+    f = oracle_pcg.pcg_fast(g1["S"], g1["Pinv"], g1["gamma"], np.zeros(6, np.float32), 2, 3, 1, 100, 1e-10)
+    np.testing.assert_allclose(f["lam"], g1["lam"], rtol=2e-3)
+    assert not f["max_iter_exit"]
+
+
+def test_fast_order_exit_semantics_match_reference_order(oracle_pcg):
+    from mpcgpu_b200 import synth
+    n, N = 14, 32
+    d = synth.make_systems(n, N, seed=21)
+    S, P, g, l0 = (d[k][0] for k in ("S", "Pinv", "gamma", "lambda0"))
+    for cap, tol in ((3, 1e-30), (0, 1e-6), (50, 1e30), (1, 1e-30)):
+        a = oracle_pcg.pcg_fast(S, P, g, l0, n, N, 4, cap, tol)
+        b = oracle_pcg.pcg(S, P, g, l0, n, N, cap, tol)
+        assert (a["iters"], a["max_iter_exit"]) == (b["iters"], b["max_iter_exit"])
+    a = oracle_pcg.pcg_fast(S, P, g, l0, n, N, 4, 0, 1e-6)
+    assert np.array_equal(a["lam"], l0)

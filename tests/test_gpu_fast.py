@@ -1,0 +1,237 @@
+"""GPU tests of the tolerance-parity ("fast") kernels -- the library's default numerics (include/gbd_pcg.h).
+
+Two bars, both through the C ABI:
+
+1. BIT-EXACT against oracle/pcg_fast_oracle.c, the CPU restatement of exactly the operation order these kernels use
+   (Chronopoulos-Gear recurrence, per-tile chains, per-CTA reductions): lambda, r, p, iteration count, exit flag.
+   A tolerance can hide a bug; this bar cannot.
+2. TOLERANCE PARITY against the reference kernel pcg<T,n,N> (GBD-PCG/include/pcg.cuh:54-218) -- its outputs stored in
+   tests/golden/iiwa_*.npz (minted on a B200 from the reference's own assembly + kernel, tools/make_golden.py), the
+   kernel itself run on this GPU when oracle/_ref is present, and the bit-faithful C oracle elsewhere -- with the
+   policy of SURVEY.md 8(c)(ii), written here:
+       iteration count within +-2 of the reference's;
+       max_iter_exit identical unless the reference is within 2 iterations of the cap;
+       max|lambda - lambda_ref| / max|lambda_ref| <= 1e-3;
+       fp64 relative residual ||gamma - S lambda|| / ||gamma|| <= 1.1 x the reference kernel's (+1e-6 absolute).
+"""
+import numpy as np
+import pytest
+
+from mpcgpu_b200 import synth
+
+pytestmark = [pytest.mark.gpu, pytest.mark.fast_numerics]
+
+ITER_TOL = 2
+LAMBDA_TOL = 1e-3
+RESID_FACTOR = 1.1
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("-m gpu tests need a CUDA device")
+    torch.cuda.init()
+    return torch
+
+
+def _dev(torch, a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _gpu_solve(torch, m, S, P, g, l0, n, N, max_iter, tol):
+    dS, dP, dg = (_dev(torch, np.asarray(x, np.float32)) for x in (S, P, g))
+    lam = _dev(torch, np.asarray(l0, np.float32))
+    r = torch.full((n * N,), float("nan"), device="cuda")
+    p = torch.full((n * N,), float("nan"), device="cuda")
+    it = torch.full((1,), -1, dtype=torch.int32, device="cuda")
+    fl = torch.full((1,), 7, dtype=torch.uint8, device="cuda")
+    m.pcg_launch(n, N, dS, dP, dg, lam, r, p, None, None, it, fl, max_iter, tol)
+    torch.cuda.synchronize()
+    return dict(lam=lam.cpu().numpy(), iters=int(it.item()), max_iter_exit=bool(fl.item()), r=r.cpu().numpy(), p=p.cpu().numpy())
+
+
+def _assert_same(a, b, what=""):
+    assert a["iters"] == b["iters"], f"{what}: iters {a['iters']} vs {b['iters']}"
+    assert a["max_iter_exit"] == b["max_iter_exit"], what
+    for k in ("lam", "r", "p"):
+        assert np.array_equal(np.asarray(a[k]), np.asarray(b[k])), f"{what}: {k} differs, max abs " \
+            f"{np.abs(np.asarray(a[k], np.float64) - np.asarray(b[k], np.float64)).max()}"
+
+
+def _assert_parity(oracle_pcg, got, ref, S, g, n, N, cap, what=""):
+    """SURVEY.md 8(c)(ii) against a reference-order result `ref` (dict with lam, iters, max_iter_exit)."""
+    assert abs(got["iters"] - ref["iters"]) <= ITER_TOL, f"{what}: iters {got['iters']} vs reference {ref['iters']}"
+    if ref["iters"] < cap - ITER_TOL or ref["max_iter_exit"]:
+        if not (ref["max_iter_exit"] is False and ref["iters"] >= cap - ITER_TOL):
+            assert got["max_iter_exit"] == ref["max_iter_exit"], what
+    scale = np.abs(ref["lam"]).max()
+    if scale > 0:
+        err = np.abs(got["lam"].astype(np.float64) - ref["lam"].astype(np.float64)).max() / scale
+        assert err <= LAMBDA_TOL, f"{what}: lambda differs from the reference by {err:.2e} (relative, max norm)"
+    r_got = oracle_pcg.rel_residual(S, g, got["lam"], n, N)
+    r_ref = oracle_pcg.rel_residual(S, g, ref["lam"], n, N)
+    assert r_got <= RESID_FACTOR * r_ref + 1e-6, f"{what}: residual {r_got:.3e} vs reference {r_ref:.3e}"
+
+
+def test_default_numerics_is_fast_and_resolves_to_a_fast_kernel(torch_cuda, capi):
+    assert capi.lib().gbd_pcg_get_numerics() == capi.NUMERICS_FAST
+    for N in (32, 64, 128, 256):
+        v = capi.resolved_variant(14, N)
+        assert v["fast"] and v["kernel"].endswith("fast"), v
+    # shapes without a fast kernel are served by the bit-exact family
+    assert not capi.resolved_variant(14, 128, f64=True)["fast"]
+    prev = capi.set_numerics(capi.NUMERICS_BITEXACT)
+    try:
+        assert not capi.resolved_variant(14, 128)["fast"]
+    finally:
+        capi.set_numerics(prev)
+
+
+def test_every_fast_variant_bit_exact_vs_its_own_oracle(torch_cuda, capi, oracle_pcg):
+    """Each compiled fast variant against the CPU restatement of its operation order; NaN pad tiles; warm start."""
+    import mpcgpu_b200 as m
+    L = capi.lib()
+    seen = 0
+    for v in capi.variants():
+        if not v["fast"] or v["mode"] not in (20, 21):
+            continue
+        n, N, C = v["n"], v["N"], v["cluster"]
+        d = synth.make_systems(n, N, batch=2, seed=300 + n + N, nan_pads=True)
+        cap, tol = (40, 1e-7) if N > 128 else (60, 1e-6)
+        assert L.gbd_pcg_set_tuning(n, N, 0, C, v["mode"]) == 0
+        try:
+            for i in range(2):
+                l0 = d["lambda0"][i] if i == 0 else (0.1 * np.random.default_rng(i).standard_normal(n * N)).astype(np.float32)
+                got = _gpu_solve(torch_cuda, m, d["S"][i], d["Pinv"][i], d["gamma"][i], l0, n, N, cap, tol)
+                want = oracle_pcg.pcg_fast(d["S"][i], d["Pinv"][i], d["gamma"][i], l0, n, N, C, cap, tol)
+                _assert_same(got, want, f"variant {v} system {i}")
+                assert np.isfinite(got["lam"]).all()
+        finally:
+            L.gbd_pcg_set_tuning(n, N, 0, 0, -1)
+        seen += 1
+    assert seen >= 8
+
+
+def test_golden_iiwa_systems_tolerance_parity_vs_reference_kernel(torch_cuda, capi, oracle_pcg):
+    """The reference's own IIWA systems and the reference kernel's own answers (tests/golden): every fast variant of the
+    size within the stated tolerance, and bit-exact against its own oracle on the real data too."""
+    import mpcgpu_b200 as m
+    from test_golden import GOLDEN, load
+    L = capi.lib()
+    checked = 0
+    for path in GOLDEN:
+        g = load(path)
+        n, N = g["n"], g["N"]
+        l0 = np.zeros(n * N, np.float32)
+        for v in [v for v in capi.variants() if v["n"] == n and v["N"] == N and v["mode"] in (20, 21)]:
+            assert L.gbd_pcg_set_tuning(n, N, 0, v["cluster"], v["mode"]) == 0
+            try:
+                for run in g["runs"]:
+                    got = _gpu_solve(torch_cuda, m, g["S"], g["Pinv"], g["gamma"], l0, n, N, run["cap"], run["tol"])
+                    _assert_parity(oracle_pcg, got, run, g["S"], g["gamma"], n, N, run["cap"], f"{g['name']} tol {run['tol']} {v}")
+                    want = oracle_pcg.pcg_fast(g["S"], g["Pinv"], g["gamma"], l0, n, N, v["cluster"], run["cap"], run["tol"])
+                    _assert_same(got, want, f"{g['name']} own oracle {v}")
+                    checked += 1
+            finally:
+                L.gbd_pcg_set_tuning(n, N, 0, 0, -1)
+    assert checked >= 8
+
+
+@pytest.mark.parametrize("n,N,cap,tol", [(14, 32, 173, 1e-6), (14, 64, 167, 1e-5), (14, 128, 167, 1e-4), (14, 128, 167, 1e-6),
+                                         (14, 256, 118, 1e-5), (6, 12, 60, 1e-6), (2, 3, 50, 1e-10)])
+def test_synthetic_rings_tolerance_parity(torch_cuda, capi, oracle_pcg, n, N, cap, tol):
+    """Default (fast) launch vs the bit-faithful reference oracle and, when present, the unmodified reference kernel on this GPU."""
+    import mpcgpu_b200 as m
+    from oracle import refgpu
+    torch = torch_cuda
+    d = synth.make_systems(n, N, batch=3, seed=40 + N, nan_pads=True)
+    for i in range(3):
+        S, P, g, l0 = (d[k][i] for k in ("S", "Pinv", "gamma", "lambda0"))
+        got = _gpu_solve(torch, m, S, P, g, l0, n, N, cap, tol)
+        ref = oracle_pcg.pcg(S, P, g, l0, n, N, cap, tol)
+        _assert_parity(oracle_pcg, got, ref, S, g, n, N, cap, f"({n},{N}) system {i} vs oracle")
+        if i == 0 and refgpu.available():
+            rk = refgpu.solve(n, N, _dev(torch, S), _dev(torch, P), _dev(torch, g), _dev(torch, l0), cap, tol, block=128)
+            rk = dict(lam=rk["lam"].cpu().numpy(), iters=rk["iters"], max_iter_exit=rk["max_iter_exit"])
+            _assert_parity(oracle_pcg, got, rk, S, g, n, N, cap, f"({n},{N}) vs reference kernel")
+
+
+def test_exit_semantics_and_warm_start(torch_cuda, capi, oracle_pcg):
+    """pcg.cuh:195,212: iters = k+1 when iteration k passed the test, max_iter with the flag set otherwise; lambda is in/out."""
+    import mpcgpu_b200 as m
+    n, N = 14, 32
+    C = capi.resolved_variant(n, N)["cluster"]
+    d = synth.make_systems(n, N, seed=21)
+    S, P, g, l0 = (d[k][0] for k in ("S", "Pinv", "gamma", "lambda0"))
+    for cap, tol in ((3, 1e-30), (0, 1e-6), (50, 1e30), (1, 1e-30)):
+        got = _gpu_solve(torch_cuda, m, S, P, g, l0, n, N, cap, tol)
+        ref = oracle_pcg.pcg(S, P, g, l0, n, N, cap, tol)
+        assert (got["iters"], got["max_iter_exit"]) == (ref["iters"], ref["max_iter_exit"])
+        _assert_same(got, oracle_pcg.pcg_fast(S, P, g, l0, n, N, C, cap, tol), f"cap {cap} tol {tol}")
+    full = _gpu_solve(torch_cuda, m, S, P, g, l0, n, N, 173, 1e-7)
+    warm = _gpu_solve(torch_cuda, m, S, P, g, full["lam"], n, N, 173, 1e-7)
+    assert warm["iters"] < full["iters"]
+    _assert_same(warm, oracle_pcg.pcg_fast(S, P, g, full["lam"], n, N, C, 173, 1e-7), "warm start")
+
+
+def test_batched_equals_single_and_is_deterministic(torch_cuda, capi, oracle_pcg):
+    """More systems than resident clusters, iteration counts from 1 to the cap (right-hand sides over six decades): clusters
+    draw systems from the work counter in a data-dependent order, yet every system equals its own-oracle solution bit for
+    bit, lands in its slot, and a second launch reproduces the first."""
+    import mpcgpu_b200 as m
+    torch = torch_cuda
+    n, N, B, cap, tol = 14, 32, 300, 60, 1e-4
+    C = capi.resolved_variant(n, N, batched=True)["cluster"]
+    d = synth.make_systems(n, N, batch=B, seed=77, nan_pads=True)
+    scale = (10.0 ** np.random.default_rng(5).uniform(-4.0, 2.0, size=B)).astype(np.float32)
+    gam = (d["gamma"] * scale[:, None]).astype(np.float32)
+    S, P, g = (_dev(torch, x) for x in (d["S"], d["Pinv"], gam))
+    outs = []
+    for _ in range(2):
+        lam = _dev(torch, d["lambda0"])
+        it = torch.zeros(B, dtype=torch.int32, device="cuda")
+        fl = torch.zeros(B, dtype=torch.uint8, device="cuda")
+        m.solve_batched(n, N, B, S, P, g, lam, it, fl, cap, tol)
+        torch.cuda.synchronize()
+        outs.append((lam.cpu().numpy(), it.cpu().numpy(), fl.cpu().numpy()))
+    assert all(np.array_equal(a, b) for a, b in zip(outs[0], outs[1]))
+    lam, it, fl = outs[0]
+    for i in list(range(0, B, 7)) + [B - 1]:
+        want = oracle_pcg.pcg_fast(d["S"][i], d["Pinv"][i], gam[i], d["lambda0"][i], n, N, C, cap, tol)
+        assert int(it[i]) == want["iters"] and bool(fl[i]) == want["max_iter_exit"], i
+        assert np.array_equal(lam[i], want["lam"]), i
+    assert it.min() <= 5 and fl.any()
+
+
+def test_full_size_batch_properties(torch_cuda, capi, oracle_pcg):
+    """BASELINE config 4 size (1024 x N=128): every system's fp64 residual is within the parity bound of the bit-exact
+    kernels' on the same batch, iteration counts within +-2, on all 1024 systems (GPU vs GPU)."""
+    import mpcgpu_b200 as m
+    torch = torch_cuda
+    n, N, B, cap, tol = 14, 128, 1024, 167, 1e-4
+    d = synth.make_systems(n, N, batch=B, seed=11)
+    S, P, g = (_dev(torch, d[k]) for k in ("S", "Pinv", "gamma"))
+    res = {}
+    for name, num in (("fast", capi.NUMERICS_FAST), ("exact", capi.NUMERICS_BITEXACT)):
+        prev = capi.set_numerics(num)
+        try:
+            lam = _dev(torch, d["lambda0"])
+            it = torch.zeros(B, dtype=torch.int32, device="cuda")
+            fl = torch.zeros(B, dtype=torch.uint8, device="cuda")
+            m.solve_batched(n, N, B, S, P, g, lam, it, fl, cap, tol)
+            torch.cuda.synchronize()
+            res[name] = (lam.cpu().numpy(), it.cpu().numpy(), fl.cpu().numpy())
+        finally:
+            capi.set_numerics(prev)
+    lf, itf, ff = res["fast"]
+    le, ite, fe = res["exact"]
+    assert np.abs(itf.astype(int) - ite.astype(int)).max() <= ITER_TOL
+    near_cap = ite >= cap - ITER_TOL
+    assert np.array_equal(ff[~near_cap], fe[~near_cap])
+    err = np.abs(lf.astype(np.float64) - le).max(axis=1) / np.abs(le).max(axis=1)
+    assert err.max() <= LAMBDA_TOL, err.max()
+    for i in range(0, B, 64):
+        rf = oracle_pcg.rel_residual(d["S"][i], d["gamma"][i], lf[i], n, N)
+        re_ = oracle_pcg.rel_residual(d["S"][i], d["gamma"][i], le[i], n, N)
+        assert rf <= RESID_FACTOR * re_ + 1e-6
