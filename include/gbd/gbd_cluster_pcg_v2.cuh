@@ -431,6 +431,10 @@ __device__ __forceinline__ void pcg_cluster_v2_run(const PcgArgs<T> &a, unsigned
             store_result(a, sys, iter, max_iter_exit);
         }
         cta_sync();
+        // batches: no CTA starts the next system's exchanges while a peer may still be reading this system's last packets /
+        // phases (neighbour-only prologue exchanges do not order far CTAs).  Once per solve, off the iteration path; the
+        // drop-in pcg<> (batch == 1, extra idle threads in the block) never gets here.
+        if (a.batch > 1) cluster_sync();
     }
     (void)first_row; (void)last_row;
 }

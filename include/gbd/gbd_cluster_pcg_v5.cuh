@@ -312,6 +312,10 @@ __device__ __forceinline__ void pcg_cluster_v5_run(const PcgArgs<float> &a, unsi
             store_result(a, sys, iter, max_iter_exit);
         }
         cta_sync();
+        // batches: no CTA starts the next system's exchanges while a peer may still be reading this system's last packets /
+        // phases (neighbour-only prologue exchanges do not order far CTAs).  Once per solve, off the iteration path; the
+        // drop-in pcg<> (batch == 1, extra idle threads in the block) never gets here.
+        if (a.batch > 1) cluster_sync();
         if (draw) {
             uint64_t q;
             uint32_t spins = 0;

@@ -16,6 +16,8 @@
 // PCG solution (golden vectors for rows f1 / f2, tools/make_golden_schur.py).
 // count > 1 with perturb = 1 builds BASELINE config 4's batch: system i = the window at <offset> plus
 // N(0, 0.05^2) on q, N(0, 0.01^2) on qd, N(0, 1) on u, std::mt19937_64(1234 + i).
+// perturb = 2 slides the window instead: system i = the window at <offset> + i * <stride> (argv[8], default 1), no noise --
+// the ring of distinct real systems bench.py solves (what successive MPC steps of examples/track_iiwa_pcg.cu assemble).
 #include <cstdio>
 #include <fstream>
 #include <iostream>
@@ -35,17 +37,24 @@ int main(int argc, char **argv)
     constexpr uint32_t state_size = grid::NUM_JOINTS * 2, control_size = grid::NUM_JOINTS, knot_points = KNOT_POINTS;
     const linsys_t timestep = .015625;
     const uint32_t offset = atoi(argv[4]), count = atoi(argv[5]);
-    const bool perturb = atoi(argv[6]) != 0;
+    const bool perturb = atoi(argv[6]) == 1, slide = atoi(argv[6]) == 2;
+    const uint32_t stride = argc > 8 ? atoi(argv[8]) : 1;
     auto xu2d = readCSVToVecVec<linsys_t>(argv[1]);
     auto ee2d = readCSVToVecVec<linsys_t>(argv[2]);
-    if (xu2d.size() < offset + knot_points || ee2d.size() < offset + knot_points) { fprintf(stderr, "trajectory too short\n"); return 3; }
+    const uint32_t last_offset = offset + (slide ? (count - 1) * stride : 0);
+    if (xu2d.size() < last_offset + knot_points || ee2d.size() < last_offset + knot_points) { fprintf(stderr, "trajectory too short\n"); return 3; }
     std::vector<linsys_t> xu0, ee;
-    for (uint32_t k = 0; k < knot_points; k++) {
-        const auto &row = xu2d[offset + k];
-        const uint32_t take = (k + 1 < knot_points) ? state_size + control_size : state_size;
-        xu0.insert(xu0.end(), row.begin(), row.begin() + take);
-        ee.insert(ee.end(), ee2d[offset + k].begin(), ee2d[offset + k].begin() + 6);
-    }
+    auto load_window = [&](uint32_t off) {
+        xu0.clear();
+        ee.clear();
+        for (uint32_t k = 0; k < knot_points; k++) {
+            const auto &row = xu2d[off + k];
+            const uint32_t take = (k + 1 < knot_points) ? state_size + control_size : state_size;
+            xu0.insert(xu0.end(), row.begin(), row.begin() + take);
+            ee.insert(ee.end(), ee2d[off + k].begin(), ee2d[off + k].begin() + 6);
+        }
+    };
+    load_window(offset);
     const uint32_t traj_len = (state_size + control_size) * knot_points - control_size;
     const uint32_t states_sq = state_size * state_size, controls_sq = control_size * control_size;
     const size_t G_bytes = ((states_sq + controls_sq) * knot_points - controls_sq) * sizeof(linsys_t);
@@ -95,6 +104,10 @@ int main(int argc, char **argv)
     if (fk) gpuErrchk(cudaMalloc(&d_dz, g_bytes));
     std::vector<linsys_t> hS(mat), hP(mat), hg(vec);
     for (uint32_t i = 0; i < count; i++) {
+        if (slide && i > 0) {
+            load_window(offset + i * stride);
+            gpuErrchk(cudaMemcpy(d_ee, ee.data(), 6 * knot_points * sizeof(linsys_t), cudaMemcpyHostToDevice));
+        }
         std::vector<linsys_t> xu = xu0;
         if (perturb) {
             std::mt19937_64 gen(1234 + i);
@@ -162,6 +175,7 @@ int main(int argc, char **argv)
     }
     fclose(f);
     if (fk) fclose(fk);
-    printf("captured %u system(s): n=%u N=%u offset=%u perturb=%d -> %s\n", count, state_size, knot_points, offset, (int)perturb, argv[3]);
+    printf("captured %u system(s): n=%u N=%u offset=%u perturb=%d slide=%d stride=%u -> %s\n", count, state_size, knot_points, offset,
+           (int)perturb, (int)slide, stride, argv[3]);
     return 0;
 }
