@@ -143,7 +143,7 @@ Variant *find_variant(uint32_t n, uint32_t N, bool f64, bool batched)
         Variant *grid = nullptr;
         for (auto &v : variants()) {
             if (v.n != n || v.N != N || v.f64 != f64 || v.unusable || mode_is_fast(v.mode) != want_fast) continue;
-            if (v.mode == 10 || v.mode == 14 || v.mode == gbdlib::MODE_FAST_PROF) continue;      // timeline builds are never a default
+            if (v.mode == 10 || v.mode == 14 || v.mode == gbdlib::MODE_FAST_PROF || v.mode == 23) continue;      // timeline / A-B builds are never a default
             if (mode_is_grid(v.mode)) { if (!grid) grid = &v; continue; }                          // whole-GPU kernels last
             return &v;
         }

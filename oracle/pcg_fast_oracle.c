@@ -14,9 +14,10 @@
  *   band row    three per-tile chains (first term a product, then one FMA per column, ascending), then
  *               (left + diag) + right; pad tiles and rows outside the system contribute exact zeros
  *   dots        per CTA of R = N/C own knot rows laid out in 16-lane groups (group 0 = the halo row a-1,
- *               contributing zeros), 32-lane XOR butterfly 16,8,4,2,1 per warp, the CTA's warps summed in
- *               ascending order, the C CTA partials summed 4 per lane in ascending order and then by an
- *               XOR butterfly over C/4 lanes
+ *               contributing zeros): the NT per-thread products are added by eight lanes, lane l taking the
+ *               pairs {16m + 2l, 16m + 2l + 1} in a balanced tree, then an XOR butterfly 4,2,1 over the eight;
+ *               the C CTA partials are summed 4 per lane in ascending order and then by an XOR butterfly
+ *               over C/4 lanes
  *   scalars     correctly rounded reciprocals (1.0f/x) times products, FMAs as written
  *
  * Layout as in pcg_oracle.c: S, Pinv = [N][3][n][n], column-major tiles, tiles (0,left), (N-1,right) unused.
@@ -57,27 +58,36 @@ static void band(uint32_t n, uint32_t N, const float *M, const float *x, float *
 /* the kernels' reduction of per-element products a[i]*b[i] (i over N*n) for cluster size C */
 static float dot_fast(uint32_t n, uint32_t N, uint32_t C, const float *a, const float *b)
 {
-    const uint32_t R = N / C, NG = R + 2, NT = (NG * 16 + 31) / 32 * 32, NW = NT / 32;
+    const uint32_t R = N / C, NG = R + 2, NT = (NG * 16 + 31) / 32 * 32, PPL = NT / 16;
     float part[16];
+    float *prod = (float *)malloc(NT * sizeof(float));
     for (uint32_t cr = 0; cr < C; cr++) {
-        float cta = 0.0f;
-        for (uint32_t w = 0; w < NW; w++) {
-            float v[32];
-            for (uint32_t l = 0; l < 32; l++) {
-                const uint32_t t = w * 32 + l, g = t / 16, j = t % 16;
-                const int own = g >= 1 && g <= R && j < n;
-                const size_t i = ((size_t)cr * R + (g - 1)) * n + j;
-                v[l] = own ? a[i] * b[i] : 0.0f;
-            }
-            for (uint32_t s = 16; s >= 1; s >>= 1) {
-                float nv[32];
-                for (uint32_t l = 0; l < 32; l++) nv[l] = v[l] + v[l ^ s];
-                memcpy(v, nv, sizeof v);
-            }
-            cta = w == 0 ? v[0] : cta + v[0];
+        /* thread t = 16 g + j parks its product; group 0 and R+1 (halo rows), lanes j >= n and padding threads park zeros */
+        for (uint32_t t = 0; t < NT; t++) {
+            const uint32_t g = t / 16, j = t % 16;
+            const int own = g >= 1 && g <= R && j < n;
+            const size_t i = ((size_t)cr * R + (g - 1)) * n + j;
+            prod[t] = own ? a[i] * b[i] : 0.0f;
         }
-        part[cr] = cta;
+        /* eight lanes: lane l adds the pairs {16 m + 2 l, 16 m + 2 l + 1}, m < PPL, in a balanced tree */
+        float lanev[8];
+        for (uint32_t l = 0; l < 8; l++) {
+            float v[64];
+            for (uint32_t m = 0; m < PPL; m++) v[m] = prod[16 * m + 2 * l] + prod[16 * m + 2 * l + 1];
+            for (uint32_t cnt = PPL; cnt > 1; cnt = (cnt + 1) / 2) {
+                for (uint32_t i = 0; i < cnt / 2; i++) v[i] = v[2 * i] + v[2 * i + 1];
+                if (cnt & 1u) v[cnt / 2] = v[cnt - 1];
+            }
+            lanev[l] = v[0];
+        }
+        for (uint32_t s = 4; s >= 1; s >>= 1) {
+            float nv[8];
+            for (uint32_t l = 0; l < 8; l++) nv[l] = lanev[l] + lanev[l ^ s];
+            memcpy(lanev, nv, sizeof nv);
+        }
+        part[cr] = lanev[0];
     }
+    free(prod);
     const uint32_t PERQ = C < 4 ? C : 4, LQ = C / PERQ;
     float lanev[4];
     for (uint32_t l = 0; l < LQ; l++) {

@@ -94,7 +94,7 @@ def test_every_fast_variant_bit_exact_vs_its_own_oracle(torch_cuda, capi, oracle
     L = capi.lib()
     seen = 0
     for v in capi.variants():
-        if not v["fast"] or v["mode"] not in (20, 21):
+        if not v["fast"] or v["mode"] not in (20, 21, 23):
             continue
         n, N, C = v["n"], v["N"], v["cluster"]
         d = synth.make_systems(n, N, batch=2, seed=300 + n + N, nan_pads=True)
@@ -124,7 +124,7 @@ def test_golden_iiwa_systems_tolerance_parity_vs_reference_kernel(torch_cuda, ca
         g = load(path)
         n, N = g["n"], g["N"]
         l0 = np.zeros(n * N, np.float32)
-        for v in [v for v in capi.variants() if v["n"] == n and v["N"] == N and v["mode"] in (20, 21)]:
+        for v in [v for v in capi.variants() if v["n"] == n and v["N"] == N and v["mode"] in (20, 21, 23)]:
             assert L.gbd_pcg_set_tuning(n, N, 0, v["cluster"], v["mode"]) == 0
             try:
                 for run in g["runs"]:

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Per-phase timeline of the fast cluster kernel from its timeline build (mode 22): %clock stamps of iterations 8..11,
-reduced to mean / min / max cycles per interval over all threads.  Diagnostic tool; prints a table and writes
+"""Per-phase timeline of the fast cluster kernel from its timeline build (mode 22): every thread keeps %clock stamps of ONE
+iteration (iteration 9) in registers and writes them after the solve, so the stamped iteration runs the same instruction
+stream as the others.  Prints mean / min / max cycles per interval over all threads and writes
 gpurun_out/timeline_fast_<N>_<C>.json."""
 import json
 import os
@@ -14,10 +15,15 @@ sys.path.insert(0, ROOT)
 import mpcgpu_b200 as m  # noqa: E402
 from mpcgpu_b200 import _capi, synth  # noqa: E402
 
-NAMES = ["updates done -> r stored, CTA barrier 1 passed", "-> u = Pinv r chain done, u stored", "-> CTA barrier 2 passed",
-         "-> w = S u chain done", "-> halo sent + warp butterfly done", "(warp 0) -> warp partials polled, CTA pair sent",
-         "butterfly done -> all packets seen (poll exit)", "-> totals", "-> exit test, beta, alpha", "-> p, s, lambda, r updates (next top)"]
-NS = 10
+NS = 12
+# stamp points: 0 top (alpha known) | 1 r stored, barrier 1 passed | 2 u chain done, u stored | 3 barrier 2 passed | 4 w chain done
+# 5 (warp 0) products parked, named barrier passed | 6 (warp 0) CTA pair sent | 7 boundary rows sent | 8 poll exit | 9 totals | 10 scalars
+SEGS = [("top -> updates, r stored, CTA barrier 1", 0, 1, None), ("-> u = Pinv r chain, u stored", 1, 2, None),
+        ("-> CTA barrier 2", 2, 3, None), ("-> w = S u chain", 3, 4, None),
+        ("(warp 0) -> products parked, named barrier", 4, 5, "w0"), ("(warp 0) -> tree + 3 shuffle levels, pair sent", 5, 6, "w0"),
+        ("w chain -> boundary rows sent (all warps)", 4, 7, None), ("-> all packets seen (poll exit)", 7, 8, None),
+        ("(warp 0) pair sent -> poll exit", 6, 8, "w0"), ("-> totals", 8, 9, None), ("-> exit test, beta, den, alpha", 9, 10, None),
+        ("whole iteration: top -> scalars done", 0, 10, None)]
 
 
 def main():
@@ -30,7 +36,7 @@ def main():
         nt = v[0]["threads"]
         d = synth.make_systems(n, N, batch=1, seed=5)
         S, P, g = (torch.from_numpy(d[k][0]).cuda() for k in ("S", "Pinv", "gamma"))
-        dbg = torch.zeros(4 * NS * C * nt, dtype=torch.int32, device="cuda")
+        dbg = torch.zeros(NS * C * nt, dtype=torch.int32, device="cuda")
         it = torch.zeros(1, dtype=torch.int32, device="cuda")
         fl = torch.zeros(1, dtype=torch.uint8, device="cuda")
         assert L.gbd_pcg_set_tuning(n, N, 0, C, 22) == 0
@@ -41,32 +47,32 @@ def main():
         torch.cuda.synchronize()
         L.gbd_pcg_set_debug_buffer(None)
         L.gbd_pcg_set_tuning(n, N, 0, 0, -1)
-        a = dbg.cpu().numpy().astype(np.int64).reshape(4, NS, C * nt)
-        w0 = (np.arange(C * nt) % nt) < 32           # threads of warp 0 (the only ones that stamp point 6)
-
-        def diff(x, y):
-            return (x - y) & 0xFFFFFFFF
-
-        ivals = [diff(a[:, 1], a[:, 0]), diff(a[:, 2], a[:, 1]), diff(a[:, 3], a[:, 2]), diff(a[:, 4], a[:, 3]), diff(a[:, 5], a[:, 4]),
-                 diff(a[:, 6], a[:, 5])[:, w0], diff(a[:, 7], a[:, 5]), diff(a[:, 8], a[:, 7]), diff(a[:, 9], a[:, 8]),
-                 diff(a[1:, 0], a[:-1, 9])]
+        a = dbg.cpu().numpy().astype(np.int64).reshape(NS, C, nt)
+        w0 = np.zeros((C, nt), bool)
+        w0[:, :32] = True
         rows = []
         print(f"--- fast n={n} N={N} C={C} threads={nt} iters={int(it.item())}")
-        for name, dt in zip(NAMES, ivals):
+        for name, p0, p1, sel in SEGS:
+            dt = (a[p1] - a[p0]) & 0xFFFFFFFF
+            dt = dt[w0] if sel == "w0" else dt.reshape(-1)
             rows.append(dict(interval=name, mean=float(dt.mean()), min=int(dt.min()), max=int(dt.max())))
-            print(f"{name:58s} mean {dt.mean():7.1f}  min {dt.min():5d}  max {dt.max():5d}")
-        per_iter = diff(a[1:, 0], a[:-1, 0])
-        print(f"iteration (top to top)                                     mean {per_iter.mean():7.1f}  min {per_iter.min()}  max {per_iter.max()}")
+            print(f"{name:52s} mean {dt.mean():7.1f}  min {dt.min():5d}  max {dt.max():5d}")
         cta = 1 if C > 1 else 0
-        print("per-warp interval means, CTA %d (columns = warps):" % cta)
-        for i, name in enumerate(NAMES):
-            if i in (5, 9):
+        print("per-warp means, CTA %d (columns = warps):" % cta)
+        for name, p0, p1, sel in SEGS:
+            if sel:
                 continue
-            dt = ivals[i].reshape(4, C, nt)[:, cta, :].reshape(4, nt // 32, 32)
-            print(f"  {name:56s}", np.round(dt.mean(axis=(0, 2))).astype(int))
+            dt = ((a[p1] - a[p0]) & 0xFFFFFFFF)[cta].reshape(nt // 32, 32)
+            print(f"  {name:50s}", np.round(dt.mean(axis=1)).astype(int))
+        # skew between CTAs: when does each CTA's warp 0 send, when does each CTA leave the poll (relative to the earliest top)
+        t0 = a[0].min()
+        print("per-CTA: top / pair sent / poll exit, cycles after the earliest top")
+        print("  top      ", (a[0][:, 0] - t0))
+        print("  sent     ", (a[6][:, 0] - t0))
+        print("  poll exit", (a[8].max(axis=1) - t0))
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         with open(os.path.join(ROOT, "gpurun_out", f"timeline_fast_{N}_{C}.json"), "w") as f:
-            json.dump(dict(n=n, N=N, C=C, threads=nt, intervals=rows, iteration_cycles=float(per_iter.mean())), f, indent=1)
+            json.dump(dict(n=n, N=N, C=C, threads=nt, intervals=rows), f, indent=1)
 
 
 if __name__ == "__main__":
