@@ -56,8 +56,10 @@ const Pref g_prefs[] = {
     // tolerance parity, single solve
     {14, 128, true, false, 16, 20},  {14, 128, true, false, 8, 20},   {14, 32, true, false, 4, 20},
     {14, 64, true, false, 8, 20},    {14, 256, true, false, 16, 20},
-    // tolerance parity, batched
-    {14, 128, true, true, 8, 20},    {14, 32, true, true, 2, 20},     {14, 64, true, true, 4, 20},
+    // tolerance parity, batched: the single-solve fast kernels keep one system per 8-16 SMs and lose to the bit-exact v5 kernel
+    // on throughput (131 K vs 210 K systems/s at 1024 x N = 128, profiles/r02_ab_batched.log), so batches of these shapes
+    // stay on v5 until a batched fast kernel is listed here
+    {14, 128, true, true, 4, 11},    {14, 32, true, true, 2, 20},     {14, 32, true, true, 2, 11},
 };
 
 struct Tuning { uint32_t n, N; bool f64; uint32_t C; int mode; };
@@ -140,10 +142,11 @@ Variant *find_variant(uint32_t n, uint32_t N, bool f64, bool batched)
                     Variant *v = lookup(n, N, false, p.C, p.mode);
                     if (v && !v->unusable) return v;
                 }
+        if (want_fast && batched) continue;                 // batches: only the measured preferences above, else bit-exact
         Variant *grid = nullptr;
         for (auto &v : variants()) {
             if (v.n != n || v.N != N || v.f64 != f64 || v.unusable || mode_is_fast(v.mode) != want_fast) continue;
-            if (v.mode == 10 || v.mode == 14 || v.mode == gbdlib::MODE_FAST_PROF || v.mode == 23) continue;      // timeline / A-B builds are never a default
+            if (v.mode == 10 || v.mode == 14 || v.mode == gbdlib::MODE_FAST_PROF) continue;      // timeline builds are never a default
             if (mode_is_grid(v.mode)) { if (!grid) grid = &v; continue; }                          // whole-GPU kernels last
             return &v;
         }

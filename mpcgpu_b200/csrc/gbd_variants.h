@@ -19,7 +19,7 @@ namespace gbdlib {
 //      10 = v4 timeline build, 14 = v2 timeline build (%clock stamps of iterations 8..11 into gbd_pcg_set_debug_buffer())
 //   tolerance-parity family (GBD_PCG_NUMERICS_FAST; include/gbd/gbd_cluster_pcg_fast.cuh):
 //      20 = fast cluster kernel (single-exchange recurrence, per-CTA reductions), 1 CTA/SM; 21 = 2 CTAs/SM budget;
-//      22 = its timeline build; 23 = A/B build with one element per boundary-row packet; 24 = fast grid kernel (n = 64: whole GPU on one system)
+//      22 = its timeline build; 24 = fast grid kernel (n = 64: whole GPU on one system)
 //      26 = fast batched kernel (one system per CTA pair, Pinv rows in shared memory)
 constexpr int MODE_GRID = 4, MODE_FAST = 20, MODE_FAST2 = 21, MODE_FAST_PROF = 22, MODE_FAST_GRID = 24, MODE_FAST_BATCH = 26;
 inline bool mode_is_fast(int mode) { return mode >= 20; }

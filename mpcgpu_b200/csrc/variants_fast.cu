@@ -5,12 +5,12 @@
 namespace gbdlib {
 using namespace gbd;
 
-template <uint32_t n, uint32_t N, uint32_t C, uint32_t MINB, bool PROF = false, bool HALO3 = true>
+template <uint32_t n, uint32_t N, uint32_t C, uint32_t MINB, bool PROF = false>
 static Variant make_fast()
 {
     using K = ClusterPcgFast<n, N, C>;
-    return Variant{n, N, C, !HALO3 ? 23 : (PROF ? MODE_FAST_PROF : (MINB == 1 ? MODE_FAST : MODE_FAST2)), false, K::NT, K::SMEM_BYTES,
-                   (const void *)pcg_cluster_kernel_fast<n, N, C, MINB, PROF, HALO3>, "gbd::pcg_cluster_kernel_fast"};
+    return Variant{n, N, C, PROF ? MODE_FAST_PROF : (MINB == 1 ? MODE_FAST : MODE_FAST2), false, K::NT, K::SMEM_BYTES,
+                   (const void *)pcg_cluster_kernel_fast<n, N, C, MINB, PROF>, "gbd::pcg_cluster_kernel_fast"};
 }
 
 void register_fast(std::vector<Variant> &v)
@@ -19,9 +19,8 @@ void register_fast(std::vector<Variant> &v)
         make_fast<14, 128, 16, 1>(),  make_fast<14, 128, 8, 1>(),   make_fast<14, 32, 4, 1>(),
         make_fast<14, 32, 2, 1>(),    make_fast<14, 64, 8, 1>(),    make_fast<14, 64, 4, 1>(),
         make_fast<14, 256, 16, 1>(),  make_fast<14, 16, 4, 1>(),    make_fast<14, 8, 2, 1>(),
-        make_fast<6, 12, 3, 1>(),     make_fast<6, 12, 2, 1>(),     make_fast<2, 3, 1, 1>(),
+        make_fast<6, 12, 3, 1>(),     make_fast<6, 12, 2, 1>(),
         make_fast<14, 128, 16, 1, true>(), make_fast<14, 128, 8, 1, true>(), make_fast<14, 32, 4, 1, true>(),
-        make_fast<14, 128, 16, 1, false, false>(), make_fast<14, 32, 4, 1, false, false>(),      // A/B: one element per halo packet
     };
     for (const Variant &x : list) v.push_back(x);
 }

@@ -11,13 +11,14 @@
  *   algorithm   Chronopoulos-Gear form of preconditioned CG (same iterates as pcg.cuh:154-208 in exact
  *               arithmetic, same exit rule |r.Pinv r| < tol after every update, same iteration count and
  *               max_iter_exit meaning, pcg.cuh:195,212)
- *   band row    three per-tile chains (first term a product, then one FMA per column, ascending), then
- *               (left + diag) + right; pad tiles and rows outside the system contribute exact zeros
- *   dots        per CTA of R = N/C own knot rows laid out in 16-lane groups (group 0 = the halo row a-1,
- *               contributing zeros): the NT per-thread products are added by eight lanes, lane l taking the
- *               pairs {16m + 2l, 16m + 2l + 1} in a balanced tree, then an XOR butterfly 4,2,1 over the eight;
- *               the C CTA partials are summed 4 per lane in ascending order and then by an XOR butterfly
- *               over C/4 lanes
+ *   band row    six half-tile chains (packed FFMA2: columns 0 .. n/2-1 in the low half, n/2 .. n-1 in the high half;
+ *               first term a product, then one FMA per column, ascending), combined as
+ *               ((L.lo + D.lo) + R.lo) + ((L.hi + D.hi) + R.hi); pad tiles and rows outside the system
+ *               contribute exact zeros
+ *   dots        per CTA of R = N/C own knot rows laid out in 16-lane groups: the 16 R per-thread products are
+ *               added by eight lanes, lane l taking the products {16m + 2l, 16m + 2l + 1} and then a balanced
+ *               tree over m, then an XOR butterfly 4,2,1 over the eight; the C CTA partials are summed in a
+ *               balanced tree in ascending CTA order
  *   scalars     correctly rounded reciprocals (1.0f/x) times products, FMAs as written
  *
  * Layout as in pcg_oracle.c: S, Pinv = [N][3][n][n], column-major tiles, tiles (0,left), (N-1,right) unused.
@@ -30,55 +31,66 @@
 
 #define ORACLE_API __attribute__((visibility("default")))
 
-/* one band row (knot row b, element j) of M times x; x is the global vector, rows outside [0,N) read as zero */
-static float chain3(uint32_t n, uint32_t N, const float *M, const float *x, int b, uint32_t j)
+/* one band row (knot row b, element j) of M times x; x is the global vector, rows outside [0,N) read as zero.
+ * Per tile two half chains (columns 0 .. n/2-1 and n/2 .. n-1: the two halves of the kernel's packed FFMA2), each a product
+ * followed by one FMA per column; combined as ((L.lo + D.lo) + R.lo) + ((L.hi + D.hi) + R.hi). */
+static float chain_pairs(uint32_t n, uint32_t N, const float *M, const float *x, int b, uint32_t j)
 {
-    float acc[3];
+    const uint32_t H = n / 2;
+    float lo[3], hi[3];
     for (int blk = 0; blk < 3; blk++) {
         const int kb = b - 1 + blk;                 /* knot row the tile multiplies */
         const int zero = kb < 0 || kb >= (int)N;    /* pad tile / missing neighbour: the kernel multiplies zeros by zeros */
         const float *tile = M + ((size_t)b * 3 + blk) * n * n;
-        float s = 0.0f;
-        for (uint32_t c = 0; c < n; c++) {
-            const float m = zero ? 0.0f : tile[(size_t)c * n + j];
-            const float v = zero ? 0.0f : x[(size_t)kb * n + c];
-            s = c == 0 ? m * v : fmaf(m, v, s);
+        float sl = 0.0f, sh = 0.0f;
+        for (uint32_t c = 0; c < H; c++) {
+            const float ml = zero ? 0.0f : tile[(size_t)c * n + j], vl = zero ? 0.0f : x[(size_t)kb * n + c];
+            const float mh = zero ? 0.0f : tile[(size_t)(c + H) * n + j], vh = zero ? 0.0f : x[(size_t)kb * n + c + H];
+            sl = c == 0 ? ml * vl : fmaf(ml, vl, sl);
+            sh = c == 0 ? mh * vh : fmaf(mh, vh, sh);
         }
-        acc[blk] = s;
+        lo[blk] = sl;
+        hi[blk] = sh;
     }
-    return (acc[0] + acc[1]) + acc[2];
+    const float a = (lo[0] + lo[1]) + lo[2], c = (hi[0] + hi[1]) + hi[2];
+    return a + c;
 }
 
 static void band(uint32_t n, uint32_t N, const float *M, const float *x, float *y)
 {
     for (uint32_t b = 0; b < N; b++)
-        for (uint32_t j = 0; j < n; j++) y[(size_t)b * n + j] = chain3(n, N, M, x, (int)b, j);
+        for (uint32_t j = 0; j < n; j++) y[(size_t)b * n + j] = chain_pairs(n, N, M, x, (int)b, j);
+}
+
+/* balanced tree: (v0 + v1), (v2 + v3), ...; an odd element moves up unchanged */
+static float tree_sum(float *v, uint32_t cnt)
+{
+    for (; cnt > 1; cnt = (cnt + 1) / 2) {
+        for (uint32_t i = 0; i < cnt / 2; i++) v[i] = v[2 * i] + v[2 * i + 1];
+        if (cnt & 1u) v[cnt / 2] = v[cnt - 1];
+    }
+    return v[0];
 }
 
 /* the kernels' reduction of per-element products a[i]*b[i] (i over N*n) for cluster size C */
 static float dot_fast(uint32_t n, uint32_t N, uint32_t C, const float *a, const float *b)
 {
-    const uint32_t R = N / C, NG = R + 2, NT = (NG * 16 + 31) / 32 * 32, PPL = NT / 16;
+    const uint32_t R = N / C, NOWN = R * 16, PPL = NOWN / 16;
     float part[16];
-    float *prod = (float *)malloc(NT * sizeof(float));
+    float *prod = (float *)malloc(NOWN * sizeof(float));
     for (uint32_t cr = 0; cr < C; cr++) {
-        /* thread t = 16 g + j parks its product; group 0 and R+1 (halo rows), lanes j >= n and padding threads park zeros */
-        for (uint32_t t = 0; t < NT; t++) {
+        /* thread t = 16 g + j of the own-row warps parks its product; idle lanes j >= n hold zeros */
+        for (uint32_t t = 0; t < NOWN; t++) {
             const uint32_t g = t / 16, j = t % 16;
-            const int own = g >= 1 && g <= R && j < n;
-            const size_t i = ((size_t)cr * R + (g - 1)) * n + j;
-            prod[t] = own ? a[i] * b[i] : 0.0f;
+            const size_t i = ((size_t)cr * R + g) * n + j;
+            prod[t] = j < n ? a[i] * b[i] : 0.0f;
         }
-        /* eight lanes: lane l adds the pairs {16 m + 2 l, 16 m + 2 l + 1}, m < PPL, in a balanced tree */
+        /* eight lanes: lane l adds the products {16 m + 2 l, 16 m + 2 l + 1}, m < PPL, then a balanced tree over m */
         float lanev[8];
         for (uint32_t l = 0; l < 8; l++) {
-            float v[64];
+            float v[128];
             for (uint32_t m = 0; m < PPL; m++) v[m] = prod[16 * m + 2 * l] + prod[16 * m + 2 * l + 1];
-            for (uint32_t cnt = PPL; cnt > 1; cnt = (cnt + 1) / 2) {
-                for (uint32_t i = 0; i < cnt / 2; i++) v[i] = v[2 * i] + v[2 * i + 1];
-                if (cnt & 1u) v[cnt / 2] = v[cnt - 1];
-            }
-            lanev[l] = v[0];
+            lanev[l] = tree_sum(v, PPL);
         }
         for (uint32_t s = 4; s >= 1; s >>= 1) {
             float nv[8];
@@ -88,19 +100,7 @@ static float dot_fast(uint32_t n, uint32_t N, uint32_t C, const float *a, const 
         part[cr] = lanev[0];
     }
     free(prod);
-    const uint32_t PERQ = C < 4 ? C : 4, LQ = C / PERQ;
-    float lanev[4];
-    for (uint32_t l = 0; l < LQ; l++) {
-        float s = part[l * PERQ];
-        for (uint32_t m = 1; m < PERQ; m++) s = s + part[l * PERQ + m];
-        lanev[l] = s;
-    }
-    for (uint32_t s = LQ / 2; s >= 1; s >>= 1) {
-        float nv[4];
-        for (uint32_t l = 0; l < LQ; l++) nv[l] = lanev[l] + lanev[l ^ s];
-        memcpy(lanev, nv, sizeof nv);
-    }
-    return lanev[0];
+    return tree_sum(part, C);       /* every lane of the gathering warp adds the C pairs in the same balanced tree */
 }
 
 /*
@@ -112,7 +112,7 @@ ORACLE_API int pcg_fast_oracle_f32(uint32_t n, uint32_t N, uint32_t C, const flo
                                    uint8_t *max_iter_exit_out, float *r_out, float *p_out, float *eta_out)
 {
     if (!S || !Pinv || !gamma || !lambda || n < 2 || n > 16 || C < 1 || C > 16 || N % C || N / C < 2) return -1;
-    if (!(C < 4 || C % 4 == 0)) return -1;
+    if (n % 2 || (N / C) % 2) return -1;
     const size_t len = (size_t)n * N;
     float *buf = (float *)calloc(7 * len, sizeof(float));
     if (!buf) return -1;

@@ -26,11 +26,16 @@ def test_fast_order_within_tolerance_of_reference_kernel(oracle_pcg, path):
             assert oracle_pcg.rel_residual(g["S"], g["gamma"], f["lam"], n, N) <= 1.1 * r_ref + 1e-6
 
 
-def test_fast_order_solves_the_demo_system(oracle_pcg, g1):
-    """GBD-PCG/examples/pcg_solve.cu:14-25 (n = 2, N = 3) against the fp64 direct solution."""
-    f = oracle_pcg.pcg_fast(g1["S"], g1["Pinv"], g1["gamma"], np.zeros(6, np.float32), 2, 3, 1, 100, 1e-10)
-    np.testing.assert_allclose(f["lam"], g1["lam"], rtol=2e-3)
-    assert not f["max_iter_exit"]
+def test_fast_order_solves_a_small_system_to_fp64_truth(oracle_pcg):
+    """A well-conditioned synthetic system (n = 6, N = 12) against the fp64 block-Thomas solution."""
+    from mpcgpu_b200 import synth
+    d = synth.make_systems(6, 12, seed=3)
+    S, P, g = (d[k][0] for k in ("S", "Pinv", "gamma"))
+    for C in (2, 3):
+        f = oracle_pcg.pcg_fast(S, P, g, np.zeros(72, np.float32), 6, 12, C, 100, 1e-12)
+        assert not f["max_iter_exit"]
+        x = oracle_pcg.solve_f64(S, g, 6, 12)
+        assert np.abs(f["lam"] - x).max() / np.abs(x).max() < 1e-3
 
 
 def test_fast_order_exit_semantics_match_reference_order(oracle_pcg):

@@ -84,13 +84,27 @@ __global__ void __launch_bounds__(NT) hop(uint32_t phases, uint32_t *out, long l
         if (HALO > 0 && warp == ((MODE & 4) ? 0 : 2) && (int)lane < HALO) {
             if (hasr) { if (MODE & 1) st8w(right + par * 512, acc, ph); else st8(right + par * 512, acc, ph); }
         }
-        if (warp == 0 && (int)lane < C) {
+        if ((MODE & 512) && warp == 0) {
+            const long long w0 = clock64();
+            while (clock64() - w0 < 400) {}
+        }
+        if ((MODE & 128) && warp == 0 && (lane == 16 || lane == 17)) {
+            const bool tol = lane == 16;
+            if (tol ? hasl : hasr) st16(map_to_cta(dot_u, tol ? cr - 1 : cr + 1) + 16 * (C + (tol ? 0 : 1)) + par * 256, acc, acc + 1, ph);
+        }
+        if ((MODE & 256) && warp == 2 && lane < 2) {        // same two packets, but from another warp / instruction
+            const bool tol = lane == 0;
+            if (tol ? hasl : hasr) st16(map_to_cta(dot_u, tol ? cr - 1 : cr + 1) + 16 * (C + (tol ? 0 : 1)) + par * 256, acc, acc + 1, ph);
+        }
+        if ((MODE & 32) && warp == 0 && lane == cr) {
+            asm volatile("st.volatile.shared::cta.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dot_u + 16 * cr + par * 256), "r"(acc), "r"(ph), "r"(acc + 1), "r"(ph) : "memory");
+        } else if (warp == 0 && (int)lane < C) {
             if (DOT == 16) st16(peer + par * 256, acc, acc + 1, ph);
             else if (MODE & 1) st8w(peer + par * 256, acc, ph);
             else st8(peer + par * 256, acc, ph);
         }
         uint32_t s = 0;
-        if (!(MODE & 2) || warp == 0) {
+        if (!(MODE & 2) || warp == ((MODE & 64) ? 1 : 0)) {
             bool ok;
             uint4 q[PERQ];
             uint64_t h = 0;
@@ -107,6 +121,10 @@ __global__ void __launch_bounds__(NT) hop(uint32_t phases, uint32_t *out, long l
                         q[m].x = (uint32_t)v;
                         ok = ok && (uint32_t)(v >> 32) == ph;
                     }
+                }
+                if (MODE & (128 | 256)) {
+                    if (hasr) { const uint4 e = ld16(dot_u + 16 * (par * 16 + C)); ok = ok && e.y == ph && e.w == ph; }
+                    if (hasl) { const uint4 e = ld16(dot_u + 16 * (par * 16 + C + 1)); ok = ok && e.y == ph && e.w == ph; }
                 }
                 if (pollh) {
                     h = ld8(halo_u + 8 * (par * 64 + ((warp == 3 || (warp == 0 && (MODE & 8))) ? 0 : 32) + lane));
@@ -222,6 +240,27 @@ int main(int argc, char **argv)
     CASE(run<4, 16, 0, 128, 0>("dot only 4 warps"));
     CASE(run<4, 16, 0, 160, 2>("dot only 1 poll warp"));
     CASE(run<4, 8, 0, 160, 0>("dot 8B"));
+    CASE(run<16, 16, 0, 160, 2 + 32>("1 poller, self local"));
+    CASE(run<16, 16, 0, 160, 2 + 64>("1 poller = other warp"));
+    CASE(run<16, 16, 0, 160, 2 + 32 + 64>("other warp+self local"));
+    CASE(run<8, 16, 0, 160, 2 + 32>("1 poller, self local"));
+    CASE(run<8, 16, 0, 160, 2 + 64>("1 poller = other warp"));
+    CASE(run<4, 16, 0, 160, 2 + 32>("1 poller, self local"));
+    CASE(run<4, 16, 0, 160, 2 + 64>("1 poller = other warp"));
+    CASE(run<16, 16, 28, 160, 2 + 8>("1 poller dot+halo"));
+    CASE(run<16, 16, 28, 160, 2 + 8 + 64>("other-warp poller dot+halo"));
+    CASE(run<8, 16, 0, 160, 2 + 128>("halo in dot instr"));
+    CASE(run<8, 16, 0, 160, 2 + 256>("halo pkts other warp"));
+    CASE(run<8, 16, 0, 160, 2>("no halo (ref)"));
+    CASE(run<4, 16, 0, 160, 2 + 128>("halo in dot instr"));
+    CASE(run<4, 16, 0, 160, 2 + 256>("halo pkts other warp"));
+    CASE(run<8, 16, 0, 160, 128>("halo in dot, all poll"));
+    CASE(run<8, 16, 0, 160, 256>("halo other warp, all poll"));
+    CASE(run<8, 16, 0, 160, 2 + 512>("delay, no halo"));
+    CASE(run<8, 16, 28, 160, 2 + 8 + 512>("delay, halo 28 early"));
+    CASE(run<16, 16, 0, 160, 2 + 512>("delay, no halo"));
+    CASE(run<16, 16, 28, 160, 2 + 8 + 512>("delay, halo 28 early"));
+    CASE(run<16, 16, 28, 160, 2 + 8 + 512 + 1>("delay, halo early weak"));
     CASE(run<8, 16, 0, 288, 0>("dot only 9 warps"));
     CASE(run<8, 16, 28, 288, 0>("dot + halo 9 warps"));
     return 0;

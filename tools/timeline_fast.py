@@ -16,14 +16,17 @@ import mpcgpu_b200 as m  # noqa: E402
 from mpcgpu_b200 import _capi, synth  # noqa: E402
 
 NS = 12
-# stamp points: 0 top (alpha known) | 1 r stored, barrier 1 passed | 2 u chain done, u stored | 3 barrier 2 passed | 4 w chain done
-# 5 (warp 0) products parked, named barrier passed | 6 (warp 0) CTA pair sent | 7 boundary rows sent | 8 poll exit | 9 totals | 10 scalars
-SEGS = [("top -> updates, r stored, CTA barrier 1", 0, 1, None), ("-> u = Pinv r chain, u stored", 1, 2, None),
-        ("-> CTA barrier 2", 2, 3, None), ("-> w = S u chain", 3, 4, None),
-        ("(warp 0) -> products parked, named barrier", 4, 5, "w0"), ("(warp 0) -> tree + 3 shuffle levels, pair sent", 5, 6, "w0"),
-        ("w chain -> boundary rows sent (all warps)", 4, 7, None), ("-> all packets seen (poll exit)", 7, 8, None),
-        ("(warp 0) pair sent -> poll exit", 6, 8, "w0"), ("-> totals", 8, 9, None), ("-> exit test, beta, den, alpha", 9, 10, None),
-        ("whole iteration: top -> scalars done", 0, 10, None)]
+# stamp points (own-row warps): 0 top | 1 r stored, barrier 1 arrival | 2 u chain done, u + r.u stored | 3 barrier 2 arrival | 4 w chain done
+#   5 w.u parked, arrived at named barrier 1, boundary rows sent | 9 woken by named barrier 2 (scalars published) | 10 scalars read
+# halo warp: 4 r.u reduced | 5 named barrier 1 passed (w.u parked) | 6 w.u reduced, CTA pair sent | 7 poll exit | 8 totals | 9 scalars published
+SEGS = [("top -> updates, r stored, CTA barrier 1", 0, 1, None), ("-> (barrier wait +) u = Pinv r chain, u stored", 1, 2, None),
+        ("-> (barrier wait +) w = S u chain", 3, 4, "own"), ("-> w.u parked, barrier arrive, boundary rows sent", 4, 5, "own"),
+        ("own warps asleep until the scalars are published", 5, 9, "own"), ("-> scalars read (loop top of the next iteration)", 9, 10, "own"),
+        ("halo warp: barrier 2 arrival -> r.u reduced", 3, 4, "halo"), ("halo warp: -> named barrier passed (w.u parked)", 4, 5, "halo"),
+        ("halo warp: -> w.u reduced, CTA pair sent", 5, 6, "halo"), ("halo warp: pair sent -> all C pairs seen", 6, 11, "halo"),
+        ("halo warp: pair sent -> pairs AND boundary rows seen (poll exit)", 6, 7, "halo"),
+        ("halo warp: -> totals", 7, 8, "halo"), ("halo warp: -> exit test, beta, alpha, published", 8, 9, "halo"),
+        ("whole iteration: top -> scalars known", 0, 10, None)]
 
 
 def main():
@@ -48,13 +51,13 @@ def main():
         L.gbd_pcg_set_debug_buffer(None)
         L.gbd_pcg_set_tuning(n, N, 0, 0, -1)
         a = dbg.cpu().numpy().astype(np.int64).reshape(NS, C, nt)
-        w0 = np.zeros((C, nt), bool)
-        w0[:, :32] = True
+        halo = np.zeros((C, nt), bool)
+        halo[:, nt - 32:] = True
         rows = []
         print(f"--- fast n={n} N={N} C={C} threads={nt} iters={int(it.item())}")
         for name, p0, p1, sel in SEGS:
             dt = (a[p1] - a[p0]) & 0xFFFFFFFF
-            dt = dt[w0] if sel == "w0" else dt.reshape(-1)
+            dt = dt[halo] if sel == "halo" else (dt[~halo] if sel == "own" else dt.reshape(-1))
             rows.append(dict(interval=name, mean=float(dt.mean()), min=int(dt.min()), max=int(dt.max())))
             print(f"{name:52s} mean {dt.mean():7.1f}  min {dt.min():5d}  max {dt.max():5d}")
         cta = 1 if C > 1 else 0
@@ -66,10 +69,11 @@ def main():
             print(f"  {name:50s}", np.round(dt.mean(axis=1)).astype(int))
         # skew between CTAs: when does each CTA's warp 0 send, when does each CTA leave the poll (relative to the earliest top)
         t0 = a[0].min()
-        print("per-CTA: top / pair sent / poll exit, cycles after the earliest top")
-        print("  top      ", (a[0][:, 0] - t0))
-        print("  sent     ", (a[6][:, 0] - t0))
-        print("  poll exit", (a[8].max(axis=1) - t0))
+        print("per-CTA (halo warp): top / pair sent / poll exit / published, cycles after the earliest top")
+        for nm, pt in (("top", 0), ("pair sent", 6), ("pairs seen", 7), ("published", 9), ("halo seen", 11)):
+            print(f"  {nm:10s}", (a[pt][:, nt - 1] - t0))
+        print("  halo sent (warp 0 / last own warp)", (a[5][:, 0] - t0), (a[5][:, nt - 33] - t0))
+        print("  own top   ", (a[0][:, 0] - t0))
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         with open(os.path.join(ROOT, "gpurun_out", f"timeline_fast_{N}_{C}.json"), "w") as f:
             json.dump(dict(n=n, N=N, C=C, threads=nt, intervals=rows), f, indent=1)
