@@ -3,26 +3,28 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-Workload (N=1): BASELINE.json configs[1] -- one IIWA-sized trajectory, state_size n=14,
-knot_points N=128, fp32, PCG cap 167 (include/common/settings.cuh:128-130), exit tol 1e-4
-(examples/track_iiwa_pcg.cu:62-68), synthetic Schur systems (mpcgpu_b200/synth.py).  A "step" is ONE
-linear-system solve (one pass of the hot path): step s solves system s mod RING from a ring of RING=256
-distinct device-resident systems (S+Pinv = 154 MB > 126 MB L2, so every step reads its tiles cold)
-into a fresh zero lambda.  value = solves/s summed over ranks (for N>1 every rank runs its own
-trajectory stream: the single-trajectory path does not shard, "replicas only"; the batched path does
-and is reported in the "batched" object with one NCCL all-gather of converged flags per step).
+Workload (N=1): BASELINE.json configs[1] -- the Kuka IIWA tracking problem, state_size n=14, knot_points N=128, fp32, PCG cap
+167 (include/common/settings.cuh:128-130), exit tol 1e-4 (examples/track_iiwa_pcg.cu:62-68).  INPUTS are the reference's own:
+a ring of RING=256 distinct Schur systems assembled by the reference's generate_kkt_submatrices + form_schur_system on sliding
+128-knot windows of examples/trajfiles/0_0_traj.csv (oracle/iiwa.py -> oracle/_ref/ref_capture_128, built from the reference
+headers; `data: "iiwa"`).  Where those binaries are absent the ring is synthetic (mpcgpu_b200/synth.py) and `data` says so.
+A "step" is ONE linear-system solve (one pass of the hot path): step s solves system s mod RING (S+Pinv of the ring = 147 MiB
+> 126 MB L2, so every step reads its tiles cold) into a fresh zero lambda.  value = solves/s summed over ranks (for N>1 every
+rank runs its own trajectory stream: the single-trajectory path does not shard, "replicas only"; the batched path does and is
+reported in "batched" with one NCCL all-gather of converged flags per step).
 
-  value        device-resident throughput, CUDA events on the launching stream, max over ranks
-  e2e          same solves through the host-buffer C-ABI entry (gbd_pcg_plan_solve_host_f32, the
-               solvePCG(h_S,...) replacement): pinned host inputs, H2D + solve + D2H inside the
-               timed region, wall clock with device syncs on both sides
-  roofline     dominant kernel = pcg_cluster_kernel; achieved = sum(iters) * B_iter(n,N) / event time
-               (B_iter = 4[2(3N-2)n^2 + 6Nn] bytes per PCG iteration per system).  Tiles
-               live in registers/smem across iterations, so this SpMV-equivalent figure is NOT DRAM
-               traffic; "compulsory_gbs" is the true per-solve traffic rate and "traffic" the ncu DRAM
-               bytes per launch (profiles/).
-  cpu_baseline the reference's own QDLDL (oracle/_ref) -- or the oracle PCG port if that is absent --
-               on a bounded sample of the same systems, on this box's host cores.
+  value            device-resident throughput of the library default (tolerance-parity "fast" kernels), CUDA events on the
+                   launching stream, max over ranks;  "bitexact" = the same steps with GBD_PCG_NUMERICS_BITEXACT
+  reference_gbdpcg the UNMODIFIED reference kernel pcg<float,14,128> (oracle/_ref/libref_gbdpcg.so) on the same ring, launched
+                   as include/pcg/sqp.cuh:230 does: cudaEvent kernel time + the reference's own stopwatch window (:224-241)
+  tolerance_sweep  the five pcg_exit_tol values of examples/track_iiwa_pcg.cu:62-68, ours and the reference kernel
+  e2e              the same solves through the host-buffer C-ABI entry (gbd_pcg_plan_solve_host_f32, the solvePCG(h_S,...)
+                   replacement): pinned host inputs, H2D + solve + D2H inside the timed region
+  roofline         dominant kernel (name read back from the library); achieved = sum(iters) * B_iter(n,N) / event time
+                   (B_iter = 4[2(3N-2)n^2 + 6Nn] bytes per PCG iteration per system).  Tiles live in registers
+                   across iterations, so this SpMV-equivalent figure is NOT DRAM traffic; "compulsory_gbs" is the true
+                   per-solve traffic rate and "traffic" the ncu DRAM bytes per launch of THIS kernel (profiles/ncu_summary.json)
+  cpu_baseline     the reference's own QDLDL (oracle/_ref) on a bounded sample of the same ring, on this box's host cores
 """
 from __future__ import annotations
 
@@ -40,7 +42,10 @@ sys.path.insert(0, ROOT)
 
 N_STATE, N_KNOT, MAX_ITER, EXIT_TOL = 14, 128, 167, 1e-4
 RING = 256
+RING_STRIDE = 2
 BATCH_TOTAL = 1024
+SWEEP_TOLS = (1e-5, 5e-5, 1e-4, 5e-4, 1e-3)          # examples/track_iiwa_pcg.cu:62-68
+CAPS = {32: 173, 64: 167, 128: 167, 256: 118, 512: 67}  # include/common/settings.cuh:123-138
 
 
 def _peaks():
@@ -51,13 +56,39 @@ def _peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def _ncu_traffic():
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture, or None."""
+def _ncu_traffic(kernel: str, cluster: int):
+    """DRAM bytes per launch of the named kernel from the committed ncu capture (keyed by kernel and cluster size), or None."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
-            return json.load(f).get("single_solve", {}).get("dram_bytes_per_launch")
+            for e in json.load(f).get("kernels", []):
+                if e.get("kernel") == kernel and e.get("cluster") == cluster:
+                    return e.get("dram_bytes_per_launch")
     except Exception:
-        return None
+        pass
+    return None
+
+
+def load_ring(N: int, count: int, stride: int = RING_STRIDE, seed: int = 1000):
+    """The ring of systems both arms solve: reference-minted IIWA systems when oracle/_ref has the capture binaries (needs the GPU),
+    synthetic ones otherwise.  Returns (systems dict, data label)."""
+    try:
+        from oracle import iiwa
+        if iiwa.available(N):
+            return iiwa.ring(N, count, stride), "iiwa"
+    except Exception as e:                                    # a broken capture must not take the bench line down
+        print(f"bench: IIWA capture failed ({e!r}); falling back to synthetic systems", file=sys.stderr)
+    from mpcgpu_b200 import synth
+    d = synth.make_systems(N_STATE, N, batch=count, seed=seed)
+    d["source"] = "synthetic LQR-like systems (mpcgpu_b200/synth.py), seed %d" % seed
+    return d, "synthetic"
+
+
+def workload_config(data: str, ring: int, source: str):
+    """The `config` object: identical for both arms so the driver can see they ran the same thing."""
+    return {"workload": "Kuka IIWA track: n=14, N=128, fp32, tol 1e-4, cap 167 (BASELINE.json configs[1]); one linear-system solve "
+                        "per step, lambda0 = 0", "ring": ring, "inputs": source,
+            "l2": f"ring of {ring} distinct systems = {ring * 2 * 3 * N_STATE * N_STATE * N_KNOT * 4 >> 20} MiB > L2, so each step reads cold tiles",
+            "multi_gpu": "replicas only (one trajectory stream per GPU); batched path in 'batched'", "data": data}
 
 
 class ClockSampler:
@@ -162,12 +193,14 @@ def cpu_baseline(systems, seconds: float, nthreads: int):
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference's own CPU implementation (QDLDL) on the same config and metric."""
+    """--impl reference: the reference's own CPU implementation (QDLDL) on the same config, inputs and metric."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from mpcgpu_b200 import synth
-    systems = synth.make_systems(N_STATE, N_KNOT, batch=64, seed=2024)
+    full, data = load_ring(N_KNOT, args.ring)
+    ring_n = full["S"].shape[0]
+    systems = {k: (full[k][:64] if isinstance(full[k], np.ndarray) else full[k]) for k in full}
     # one trajectory's solves are sequentially dependent and QDLDL is sequential: 1 thread is all this
     # workload can use (SURVEY.md 8d).  Each "step" is a bounded sample of solves; K steps are timed.
     per_step_s = min(2.0, max(0.02, 60.0 / max(1, args.steps + args.warmup)))
@@ -213,25 +246,26 @@ def run_reference_arm(args):
         extra["batched"] = {"traj_per_sec": nb / secb, "cores": ncores,
                             "sample": f"{nb} independent QDLDL solves over {ncores} threads"}
         # BASELINE.json configs[0]: the reference's own CPU-runnable case (knot_points = 32, include/qdldl/sqp.cuh:22-49)
-        s32 = synth.make_systems(N_STATE, 32, batch=64, seed=2025)
+        s32, d32 = load_ring(32, 64, 8, seed=2025)
         v32 = qdldl.values(s32["S"], N_STATE, 32)
         t1, _ = qdldl.time_batched(v32, s32["gamma"], N_STATE, 32, reps=1, nthreads=1)
         r32 = max(1, int(1.0 / max(t1, 1e-6)))
         t32, _ = qdldl.time_batched(v32, s32["gamma"], N_STATE, 32, reps=r32, nthreads=1)
-        extra["config0_n32"] = {"us_per_solve": 1e6 * t32 / (r32 * 64), "solves_per_sec": r32 * 64 / t32, "cores": 1,
-                                "sample": f"{r32 * 64} QDLDL factor+solve pairs, n=14 N=32, 1 thread"}
+        extra["config0_n32"] = {"us_per_solve": 1e6 * t32 / (r32 * s32["S"].shape[0]), "solves_per_sec": r32 * s32["S"].shape[0] / t32,
+                                "cores": 1, "data": d32,
+                                "sample": f"{r32 * s32['S'].shape[0]} QDLDL factor+solve pairs, n=14 N=32, 1 thread"}
+    cfg = workload_config(data, ring_n, full["source"])
+    cfg["solver"] = "QDLDL factor+solve (include/qdldl/sqp.cuh:22-49)" if have_ref else "oracle PCG port"
+    cfg["host_cores_available"] = ncores
     line = {
         "impl": "reference", "metric": "linsys_solves_per_sec", "value": value, "unit": "solves/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "linsys_us": 1e6 / value,
-        "config": {"workload": "IIWA-size single trajectory: n=14, N=128, fp32 (BASELINE.json configs[1])",
-                   "solver": "QDLDL factor+solve (include/qdldl/sqp.cuh:22-49)" if have_ref else "oracle PCG port",
-                   "host_cores_available": ncores},
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": data,
+        "linsys_us": 1e6 / value, "config": cfg,
         "cpu_baseline": {"value": value, "unit": "solves/s", "cores": nth, "kind": kind,
-                         "sample": f"{tot_n} solves in {args.steps} steps, {nth} thread(s): one per trajectory stream, as many "
-                                   f"streams as the GPU arm has replicas (one trajectory is sequential; QDLDL is "
-                                   f"single-threaded by design)"},
+                         "sample": f"{tot_n} solves in {args.steps} steps over the first 64 systems of the ring, {nth} thread(s): one per "
+                                   f"trajectory stream, as many streams as the GPU arm has replicas (one trajectory is sequential; QDLDL is "
+                                   f"single-threaded by design); factor + solve only, without the reference's D2H/H2D of include/qdldl/sqp.cuh:268-273"},
         "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -260,7 +294,9 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     L = _capi.lib()
     n, N, K, W = N_STATE, N_KNOT, args.steps, args.warmup
-    ring = args.ring
+    esz = 4
+    stream = torch.cuda.current_stream().cuda_stream
+    peak, peak_src = _peaks()
 
     def barrier():
         if world > 1:
@@ -281,23 +317,36 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    # ---------------- inputs: a ring of distinct systems, resident in HBM, larger than L2
-    host = synth.make_systems(n, N, batch=ring, seed=1000 + rank)
+    def timed_us(fn, reps, warm=10):
+        for q in range(warm):
+            fn(q)
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for q in range(reps):
+            fn(warm + q)
+        a1.record()
+        torch.cuda.synchronize()
+        return 1e3 * a0.elapsed_time(a1) / reps
+
+    # ---------------- inputs: a ring of distinct systems, resident in HBM, larger than L2 (every rank: the same ring)
+    host, data = load_ring(N, args.ring)
+    ring = host["S"].shape[0]
     dS, dP, dg = (torch.from_numpy(host[k]).to(dev) for k in ("S", "Pinv", "gamma"))
     steps_total = K + W
     lam = torch.zeros(steps_total, n * N, device=dev)
     iters = torch.zeros(steps_total, dtype=torch.int32, device=dev)
     flags = torch.zeros(steps_total, dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
-    esz = 4
 
-    def launch(step):
+    def launch(step, tol=EXIT_TOL):
         i = step % ring
-        rc = L.gbd_pcg_solve_f32(n, N, dS[i].data_ptr(), dP[i].data_ptr(), dg[i].data_ptr(), lam[step].data_ptr(),
-                                 0, 0, 0, 0, iters[step:].data_ptr(), flags[step:].data_ptr(), MAX_ITER, EXIT_TOL, stream)
+        rc = L.gbd_pcg_solve_f32(n, N, dS[i].data_ptr(), dP[i].data_ptr(), dg[i].data_ptr(), lam[step % steps_total].data_ptr(),
+                                 0, 0, 0, 0, iters[step % steps_total:].data_ptr(), flags[step % steps_total:].data_ptr(), MAX_ITER, tol, stream)
         if rc:
             raise _capi.GbdPcgError(rc, "gbd_pcg_solve_f32")
 
+    numerics_default = "fast" if L.gbd_pcg_get_numerics() == _capi.NUMERICS_FAST else "bitexact"
+    resolved = _capi.resolved_variant(n, N)
     sampler = ClockSampler(local)
     sampler.start()
     t_pre = time.perf_counter()                               # untimed pre-warm: bring clocks up under this exact load
@@ -322,13 +371,30 @@ def run_ours(args):
     ms = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop()
     it_np = iters[W:].cpu().numpy().astype(np.int64)
+    fl_np = flags[W:].cpu().numpy()
     tot_iters = sum_over_ranks(float(it_np.sum()))
     value = world * K / (ms * 1e-3)
     b_iter = synth.bytes_per_iteration(n, N, esz)
-    peak, peak_src = _peaks()
     kernel_s = ms * 1e-3 / K                                   # average launch duration (back-to-back on one stream)
     achieved = (it_np.sum() / K) * b_iter / kernel_s / 1e9     # this rank's kernel, GB/s
     compulsory = (esz * (2 * (3 * N - 2) * n * n + 3 * N * n) + esz * N * n) / kernel_s / 1e9
+
+    extras = {}
+    # ---------------- the same steps with the bit-exact kernels (identical results to the reference kernel, bit for bit)
+    if rank == 0:
+        prev = _capi.set_numerics(_capi.NUMERICS_BITEXACT)
+        try:
+            rb = _capi.resolved_variant(n, N)
+            kb = min(K, 400)
+            lam.zero_()
+            us_b = timed_us(lambda q: launch(q), kb, warm=min(W, 10))
+            itb = iters[:min(steps_total, kb)].float().mean().item()
+            extras["bitexact"] = {"what": "GBD_PCG_NUMERICS_BITEXACT on the same ring: same floating-point operation order as the reference "
+                                          "kernel, bit-identical lambda / iterations / flag (tests/test_gpu_parity.py)",
+                                  "kernel": f"{rb['kernel']} (cluster {rb['cluster']}, mode {rb['mode']})", "kernel_us": us_b,
+                                  "mean_iters": itb, "us_per_iter": us_b / max(itb, 1.0), "solves_per_sec": 1e6 / us_b}
+        finally:
+            _capi.set_numerics(prev)
 
     # ---------------- the reference's own stopwatch window (sqp.cuh:224-241), device-resident inputs
     win = []
@@ -339,6 +405,63 @@ def run_ours(args):
                                    flags[:1], MAX_ITER, EXIT_TOL)
         win.append(us)
     win = np.array(win[8:])
+
+    # ---------------- the UNMODIFIED reference GBD-PCG kernel on the same ring, same process (rank 0)
+    ref_ws = None
+    if rank == 0 and not args.no_refgpu:
+        try:
+            from oracle import refgpu
+            if refgpu.available():
+                ref_ws = refgpu.RefWorkspace(n, N)
+                rlam = torch.zeros(n * N, device=dev)
+                nsys = min(ring, 32)
+
+                def ref_launch(q, tol=EXIT_TOL):
+                    i = q % nsys
+                    rlam.zero_()
+                    refgpu.launch(n, N, dS[i], dP[i], dg[i], rlam, ref_ws, MAX_ITER, tol, 128, stream)
+
+                t_zero = timed_us(lambda q: rlam.zero_(), 200)
+                us_ref = timed_us(ref_launch, 96, warm=8) - t_zero
+                rit = []
+                for i in range(nsys):                           # its iteration counts on these systems
+                    ref_launch(i)
+                    torch.cuda.synchronize()
+                    rit.append(int(ref_ws.iters.item()))
+                wref = []
+                for q in range(40):
+                    i = q % nsys
+                    rlam.zero_()
+                    wref.append(refgpu.linsys_window(n, N, dS[i], dP[i], dg[i], rlam, ref_ws, MAX_ITER, EXIT_TOL)[2])
+                extras["reference_gbdpcg"] = {
+                    "what": "unmodified reference pcg<float,14,128> (GBD-PCG/include/pcg.cuh:54-218 compiled for sm_100a into oracle/_ref/"
+                            "libref_gbdpcg.so), cooperative launch grid 128 x 128 threads as include/pcg/sqp.cuh:230, same ring (first "
+                            f"{nsys} systems), same process",
+                    "kernel_us": us_ref, "mean_iters": float(np.mean(rit)), "us_per_iter": us_ref / max(1.0, float(np.mean(rit))),
+                    "pcg_iters_per_sec": float(np.mean(rit)) / (us_ref * 1e-6),
+                    "linsys_us": {"median": float(np.median(wref[5:])), "mean": float(np.mean(wref[5:])),
+                                  "what": "the reference's own stopwatch window include/pcg/sqp.cuh:224-241"},
+                    "ours_over_reference_kernel_time": us_ref / (1e6 * kernel_s)}
+                # ---- the five exit tolerances of examples/track_iiwa_pcg.cu:62-68: ours (default numerics) and the reference kernel
+                sweep = []
+                for tol in SWEEP_TOLS:
+                    lam[:104].zero_()                               # every solve of the sweep starts from lambda0 = 0
+                    us_o = timed_us(lambda q: launch(q, tol), 96, warm=8)
+                    ito = iters[8:104].float().mean().item()
+                    capo = float((flags[8:104] != 0).float().mean().item())
+                    us_r = timed_us(lambda q: ref_launch(q, tol), 48, warm=4) - t_zero
+                    itr = []
+                    for i in range(min(nsys, 16)):
+                        ref_launch(i, tol)
+                        torch.cuda.synchronize()
+                        itr.append(int(ref_ws.iters.item()))
+                    sweep.append({"pcg_exit_tol": tol, "ours_kernel_us": us_o, "ours_mean_iters": ito, "ours_max_iter_exit_frac": capo,
+                                  "reference_kernel_us": us_r, "reference_mean_iters": float(np.mean(itr))})
+                extras["tolerance_sweep"] = sweep
+            else:
+                extras["reference_gbdpcg"] = {"unavailable": "oracle/_ref/libref_gbdpcg.so not present (built only where /root/reference exists)"}
+        except Exception as e:                                 # never fails the bench line
+            extras["reference_gbdpcg"] = {"error": repr(e)[:300]}
 
     # ---------------- e2e: host buffers through the C ABI (pinned inputs, H2D + solve + D2H timed)
     ering = min(ring, 64)
@@ -367,12 +490,25 @@ def run_ours(args):
     h2d = esz * (2 * 3 * n * n * N + 2 * n * N)
     d2h = esz * n * N + 4 + 1
 
-    # ---------------- batched config 4: 1024 systems sharded over ranks + all-gather of converged flags
+    # ---------------- batched config 4: 1024 trajectories sharded over ranks + all-gather of converged flags
     batched = None
     if not args.no_batched:
         Bl = BATCH_TOTAL // world
-        hb = synth.make_systems(n, N, batch=Bl, seed=5000 + rank)
-        bS, bP, bg = (torch.from_numpy(hb[k]).to(dev) for k in ("S", "Pinv", "gamma"))
+        bdata = "synthetic"
+        hb = None
+        try:
+            from oracle import iiwa
+            if iiwa.available(N):
+                full_b = iiwa.perturbed(N, BATCH_TOTAL)           # every rank mints the same batch and keeps its contiguous shard
+                hb = {k: full_b[k][rank * Bl:(rank + 1) * Bl] for k in ("S", "Pinv", "gamma")}
+                bdata, bsource = "iiwa", full_b["source"]
+                del full_b
+        except Exception as e:
+            print(f"bench: IIWA batch capture failed ({e!r}); synthetic batch", file=sys.stderr)
+        if hb is None:
+            hb = synth.make_systems(n, N, batch=Bl, seed=5000 + rank)
+            bsource = "synthetic LQR-like systems (mpcgpu_b200/synth.py)"
+        bS, bP, bg = (torch.from_numpy(np.ascontiguousarray(hb[k])).to(dev) for k in ("S", "Pinv", "gamma"))
         Kb, Wb = args.batched_steps, 3
         blam = torch.zeros(Kb + Wb, Bl, n * N, device=dev)
         bit = torch.zeros(Kb + Wb, Bl, dtype=torch.int32, device=dev)
@@ -381,6 +517,7 @@ def run_ours(args):
         shard = ShardedBatch(n, N, BATCH_TOTAL, world, rank, dev)
         assert shard.local == Bl
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if Bl * 2 * 3 * n * n * N * esz < (160 << 20) else None
+        rbat = _capi.resolved_variant(n, N, batched=True)
 
         def bstep(s):
             shard.iters, shard.flags = bit[s], bfl[s]
@@ -403,18 +540,24 @@ def run_ours(args):
         bi = sum_over_ranks(float(bit[Wb:].sum().item()))
         conv = sum_over_ranks(float((bfl[Wb:] == 0).sum().item())) / (world * Bl * Kb)
         bsec = tot_ms * 1e-3 / Kb
-        batched = {"workload": f"BASELINE.json configs[3]: {BATCH_TOTAL} systems n=14 N=128 sharded {Bl}/GPU, "
-                               f"tol {EXIT_TOL:g}, cap {MAX_ITER}", "traj_per_sec": world * Bl / bsec,
+        fma_per_iter = 2 * (3 * N - 2) * n * n                   # fused multiply-adds of the two band products per system-iteration
+        batched = {"workload": f"BASELINE.json configs[3]: {BATCH_TOTAL} trajectories n=14 N=128 sharded {Bl}/GPU, tol {EXIT_TOL:g}, "
+                               f"cap {MAX_ITER}", "data": bdata, "inputs": bsource, "traj_per_sec": world * Bl / bsec,
                    "pcg_iters_per_sec": bi / Kb / bsec, "ms_per_step": 1e3 * bsec, "steps": Kb,
                    "mean_iters": bi / Kb / (world * Bl), "converged_frac": conv,
+                   "kernel": f"{rbat['kernel']} (cluster {rbat['cluster']}, mode {rbat['mode']}, numerics {'fast' if rbat['fast'] else 'bitexact'})",
                    "collective": "nccl all_gather of converged flags per step" if world > 1 else "none (1 rank)",
                    "l2": "flushed between timed steps" if flush is not None else "inputs larger than L2",
-                   "roofline": {"bound": "hbm", "achieved": bi / Kb * b_iter / bsec / 1e9 / world, "peak": peak,
-                                "unit": "GB/s", "frac": bi / Kb * b_iter / bsec / 1e9 / world / peak,
-                                "compulsory_gbs": Bl * esz * (2 * (3 * N - 2) * n * n + 4 * N * n) / bsec / 1e9}}
-        launches_b = Kb
+                   "roofline": {"bound": "hbm", "unit": "GB/s", "peak": peak,
+                                "achieved": Bl * esz * (2 * (3 * N - 2) * n * n + 4 * N * n) / bsec / 1e9,
+                                "frac": Bl * esz * (2 * (3 * N - 2) * n * n + 4 * N * n) / bsec / 1e9 / peak,
+                                "what": "COMPULSORY HBM traffic per rank (every system's tiles and vectors read once, lambda written once) / "
+                                        "step time: tiles stay in registers across iterations, so this batch is not HBM-bound",
+                                "fp32_fma_tflops": 2 * (bi / Kb / world) * fma_per_iter / bsec / 1e12,
+                                "fp32_fma_frac_of_peak": 2 * (bi / Kb / world) * fma_per_iter / bsec / 1e12 / 74.4,
+                                "fp32_peak_note": "148 SMs x 128 FMA/clk x 1.965 GHz = 74.4 TFLOP/s nominal"}}
         # ---- the same batch as whole SQP linear-system steps (row f3): KKT blocks in, dz out; assembly -> solve -> dz per
-        # shard in one enqueue (4 launches), then the flag all-gather
+        # shard in one enqueue, then the flag all-gather
         try:
             from mpcgpu_b200.sharding import ShardedStep
             mctl = n // 2
@@ -439,70 +582,48 @@ def run_ours(args):
                 torch.cuda.synchronize()
                 s_ms += max_over_ranks(s0.elapsed_time(s1))
             sit, _ = sstep.plan.results()
-            batched["sqp_step"] = {"what": "gbd_step_run_f32 per shard (form_schur_system -> pcg -> compute_dz, 4 launches, no host "
-                                           "round trip) + flag all-gather; synthetic KKT blocks (mpcgpu_b200/synth.py make_kkt_batch)",
+            batched["sqp_step"] = {"what": "gbd_step_run_f32 per shard (form_schur_system -> pcg -> compute_dz, no host round trip) + flag "
+                                           "all-gather; synthetic KKT blocks (mpcgpu_b200/synth.py make_kkt_batch)",
                                    "traj_per_sec": world * Bl / (s_ms * 1e-3 / Ks), "ms_per_step": s_ms / Ks, "steps": Ks,
                                    "mean_iters_rank0": float(sit.mean()), "converged_frac_all": float((gflags == 0).float().mean().item())}
         except Exception as e:                                 # never fails the bench line
             batched["sqp_step"] = {"error": repr(e)[:200]}
-    # ---------------- extras (rank 0): the reference-minted IIWA system and the header drop-in pcg<> under the
-    # reference's own launch geometry (cooperative, grid = N, 128 threads), both on tests/golden/iiwa_128_0.npz
-    extras = {}
-    gpath = os.path.join(ROOT, "tests", "golden", "iiwa_128_0.npz")
-    if rank == 0 and os.path.exists(gpath):
-        g = np.load(gpath)
-        gS, gP, gg = (torch.from_numpy(g[k]).to(dev) for k in ("S", "Pinv", "gamma"))
-        gl = torch.zeros(n * N, device=dev)
-
-        def gsolve():
-            gl.zero_()
-            rc = L.gbd_pcg_solve_f32(n, N, gS.data_ptr(), gP.data_ptr(), gg.data_ptr(), gl.data_ptr(), 0, 0, 0, 0,
-                                     iters[:1].data_ptr(), flags[:1].data_ptr(), MAX_ITER, EXIT_TOL, stream)
-            assert rc == 0
-
-        for _ in range(20):
-            gsolve()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        for _ in range(200):
-            gsolve()
-        g1.record()
-        torch.cuda.synchronize()
-        git = int(iters[0].item())
-        extras["iiwa_golden"] = {"system": "tests/golden/iiwa_128_0.npz (reference KKT+Schur assembly of examples/trajfiles/0_0, "
-                                           "first SQP iteration)", "iters": git, "reference_kernel_iters": int(g["run0_iters"]),
-                                 "lambda_bit_identical_to_reference_kernel": bool(np.array_equal(gl.cpu().numpy(), g["run0_lam"])),
-                                 "kernel_us": 1e3 * g0.elapsed_time(g1) / 200 - 2.0, "note": "includes a ~2 us lambda memset per solve (subtracted)"}
+    # ---------------- the header drop-in pcg<> under the reference's own launch geometry (cooperative, grid = N, 128 threads)
+    if rank == 0:
         demo = os.path.join(ROOT, "tests", "_build", "dropin_demo_128")
         if os.path.exists(demo):
             import subprocess
             import tempfile
             with tempfile.TemporaryDirectory() as td:
                 fin, fout = os.path.join(td, "in.bin"), os.path.join(td, "out.bin")
-                np.concatenate([g["S"], g["Pinv"], g["gamma"], np.zeros(n * N, np.float32)]).tofile(fin)
+                np.concatenate([host["S"][0], host["Pinv"][0], host["gamma"][0], np.zeros(n * N, np.float32)]).tofile(fin)
                 try:
                     out = subprocess.run([demo, fin, fout, str(MAX_ITER), repr(EXIT_TOL), "128", "400"], capture_output=True,
                                          text=True, timeout=120).stdout.split()
                     extras["dropin_pcg_template"] = {
                         "what": "include/gbd_dropin pcg<float,14,128> launched as include/pcg/sqp.cuh:230 does "
-                                "(cudaLaunchCooperativeKernel, grid 128, block 128)", "iters": int(out[1]),
+                                "(cudaLaunchCooperativeKernel, grid 128, block 128), first system of the ring", "iters": int(out[1]),
                         "kernel_us": float(out[5]), "us_per_iter": float(out[5]) / max(1, int(out[1]))}
                 except Exception as e:                         # the extras never fail the bench line
                     extras["dropin_pcg_template"] = {"error": repr(e)[:200]}
     # ---------------- the other BASELINE.json configs (rank 0, short): kernel time per solve and SpMV-equivalent GB/s
     if rank == 0 and not args.no_configs:
         others = []
-        for (cn, cN, ccap, ctol, what) in ((14, 32, 173, 1e-4, "configs[0] size on the GPU (n=14, N=32)"),
-                                           (14, 512, 67, 1e-4, "configs[2] long horizon (n=14, N=512)"),
+        for (cn, cN, ccap, ctol, what) in ((14, 32, CAPS[32], 1e-4, "configs[0] size on the GPU (n=14, N=32)"),
+                                           (14, 512, CAPS[512], 1e-4, "configs[2] long horizon (n=14, N=512)"),
                                            (64, 256, 200, 1e-6, "configs[4] synthetic block=64, N=256, tol 1e-6, cap 200")):
             try:
-                nsys = 8 if cn == 14 else 2
-                hc = synth.make_systems(cn, cN, batch=nsys, seed=4242)
+                if cn == 14:
+                    hc, cdata = load_ring(cN, 16, 8, seed=4242)
+                else:
+                    hc, cdata = synth.make_systems(cn, cN, batch=2, seed=4242), "synthetic"
+                nsys = hc["S"].shape[0]
                 cS, cP, cg = (torch.from_numpy(hc[k]).to(dev) for k in ("S", "Pinv", "gamma"))
                 reps = 64 if cn == 14 else 16
                 cl = torch.zeros(reps + 4, cn * cN, device=dev)
                 cit = torch.zeros(reps + 4, dtype=torch.int32, device=dev)
                 cfl = torch.zeros(reps + 4, dtype=torch.uint8, device=dev)
+                rv = _capi.resolved_variant(cn, cN)
 
                 def csolve(q):
                     i = q % nsys
@@ -522,11 +643,28 @@ def run_ours(args):
                 torch.cuda.synchronize()
                 us = 1e3 * c0.elapsed_time(c1) / reps
                 mit = float(cit[4:].float().mean().item())
-                bi = synth.bytes_per_iteration(cn, cN, esz)
-                others.append({"config": what, "kernel_us": us, "mean_iters": mit, "us_per_iter": us / max(mit, 1.0),
-                               "pcg_iters_per_sec": mit / (us * 1e-6), "converged_frac": float((cfl[4:] == 0).float().mean().item()),
-                               "spmv_equiv_gbs": mit * bi / (us * 1e-6) / 1e9, "frac_of_hbm_peak": mit * bi / (us * 1e-6) / 1e9 / peak,
-                               "bytes_per_iter": bi, "tiles_resident_on_chip": True})
+                bi_ = synth.bytes_per_iteration(cn, cN, esz)
+                entry = {"config": what, "data": cdata, "kernel": f"{rv['kernel']} (cluster {rv['cluster']}, mode {rv['mode']})",
+                         "kernel_us": us, "mean_iters": mit, "us_per_iter": us / max(mit, 1.0),
+                         "pcg_iters_per_sec": mit / (us * 1e-6), "converged_frac": float((cfl[4:] == 0).float().mean().item()),
+                         "spmv_equiv_gbs": mit * bi_ / (us * 1e-6) / 1e9, "frac_of_hbm_peak": mit * bi_ / (us * 1e-6) / 1e9 / peak,
+                         "bytes_per_iter": bi_, "tiles_resident_on_chip": True}
+                if ref_ws is not None or (not args.no_refgpu):
+                    try:
+                        from oracle import refgpu
+                        if refgpu.available() and (cn, cN) in refgpu.INSTANTIATED:
+                            ws2 = refgpu.RefWorkspace(cn, cN)
+                            rl2 = torch.zeros(cn * cN, device=dev)
+
+                            def rsolve(q):
+                                rl2.zero_()
+                                refgpu.launch(cn, cN, cS[q % nsys], cP[q % nsys], cg[q % nsys], rl2, ws2, ccap, ctol, 128, stream)
+
+                            entry["reference_kernel_us"] = timed_us(rsolve, 24 if cn == 14 else 8, warm=3)
+                            entry["reference_last_iters"] = int(ws2.iters.item())
+                    except Exception as e:
+                        entry["reference_kernel_error"] = repr(e)[:160]
+                others.append(entry)
             except Exception as e:                             # the extras never fail the bench line
                 others.append({"config": what, "error": repr(e)[:200]})
         extras["other_configs"] = others
@@ -534,47 +672,22 @@ def run_ours(args):
     if rank == 0 and not args.no_configs:
         try:
             mctl = n // 2
-            rngk = np.random.default_rng(99)
-            Gs, Cs, gs = [], [], []
-            for kk in range(N):
-                Mq = rngk.standard_normal((n, n))
-                Gs.append((Mq @ Mq.T / n + np.eye(n)).T.ravel())
-                gs.append(rngk.standard_normal(n))
-                if kk < N - 1:
-                    Mr = rngk.standard_normal((mctl, mctl))
-                    Gs.append((Mr @ Mr.T / mctl + np.eye(mctl)).T.ravel())
-                    Cs.append((np.eye(n) + rngk.standard_normal((n, n)) / 16).T.ravel())
-                    Cs.append((rngk.standard_normal((n, mctl)) / 16).T.ravel())
-                    gs.append(rngk.standard_normal(mctl))
-            kG0, kC, kg = (torch.from_numpy(np.concatenate(x).astype(np.float32)).to(dev) for x in (Gs, Cs, gs))
-            kc = torch.from_numpy((0.1 * rngk.standard_normal(n * N)).astype(np.float32)).to(dev)
+            kGb, kCb, kgb, kcb = synth.make_kkt_batch(n, mctl, N, 1, seed=99)
+            kG0, kC, kg, kc = (torch.from_numpy(np.ascontiguousarray(x).reshape(-1)).to(dev) for x in (kGb, kCb, kgb, kcb))
             kG = kG0.clone()
             kS, kP = torch.zeros(3 * n * n * N, device=dev), torch.zeros(3 * n * n * N, device=dev)
             kgam, klam = torch.zeros(n * N, device=dev), torch.randn(n * N, device=dev)
             kdz = torch.zeros((n + mctl) * (N - 1) + n, device=dev)
-
-            def t_us(fn, reps=200):
-                for _ in range(10):
-                    fn()
-                torch.cuda.synchronize()
-                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a0.record()
-                for _ in range(reps):
-                    fn()
-                a1.record()
-                torch.cuda.synchronize()
-                return 1e3 * a0.elapsed_time(a1) / reps
-
             pk = [int(x.data_ptr()) for x in (kG, kC, kg, kc, kS, kP, kgam, klam, kdz)]
 
-            def f_schur():
+            def f_schur(q):
                 kG.copy_(kG0)
                 rc = L.gbd_form_schur_system_f32(n, mctl, N, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], 1e-3, stream)
                 assert rc == 0, rc
 
-            t_cp = t_us(lambda: kG.copy_(kG0))
-            t_fs = t_us(f_schur) - t_cp
-            t_dzz = t_us(lambda: L.gbd_compute_dz_f32(n, mctl, N, pk[0], pk[1], pk[2], pk[7], pk[8], stream))
+            t_cp = timed_us(lambda q: kG.copy_(kG0), 200)
+            t_fs = timed_us(f_schur, 200) - t_cp
+            t_dzz = timed_us(lambda q: L.gbd_compute_dz_f32(n, mctl, N, pk[0], pk[1], pk[2], pk[7], pk[8], stream), 200)
             extras["sqp_neighbours"] = {
                 "what": "rows f1/f2: gbd_form_schur_system_f32 (replaces form_schur_system, include/pcg/linsys_setup.cuh:621-657) and "
                         "gbd_compute_dz_f32 (replaces compute_dz, include/common/dz.cuh:125-136), n=14 m=7 N=128, device-resident, "
@@ -582,7 +695,7 @@ def run_ours(args):
                 "form_schur_us": t_fs, "compute_dz_us": t_dzz, "launches_per_call": {"form_schur": 2, "compute_dz": 1}}
         except Exception as e:                                 # the extras never fail the bench line
             extras["sqp_neighbours"] = {"error": repr(e)[:200]}
-    # ---------------- row f4: the direct solver (block cyclic reduction) on the same ring of systems and on a 1024 batch
+    # ---------------- row f4: the direct solver (block cyclic reduction) on the same ring of systems
     if rank == 0 and not args.no_configs:
         try:
             dlam = torch.zeros(n * N, device=dev)
@@ -592,19 +705,11 @@ def run_ours(args):
                 rc = L.gbd_bcr_solve_f32(n, N, dS[i].data_ptr(), dg[i].data_ptr(), dlam.data_ptr(), stream)
                 assert rc == 0, rc
 
-            for q in range(20):
-                dsolve(q)
-            torch.cuda.synchronize()
-            d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            d0.record()
-            for q in range(400):
-                dsolve(q)
-            d1.record()
-            torch.cuda.synchronize()
+            us_d = timed_us(dsolve, 400, warm=20)
             extras["direct_solver"] = {
                 "what": "gbd_bcr_solve_f32: block cyclic reduction in one 16-CTA cluster, no preconditioner, no iteration cap "
                         "(GPU alternative to the reference's CPU QDLDL path; accuracy and A/B in profiles/r01c_ab_direct.json)",
-                "kernel_us": 1e3 * d0.elapsed_time(d1) / 400, "solves_per_sec": 400 / (d0.elapsed_time(d1) * 1e-3)}
+                "kernel_us": us_d, "solves_per_sec": 1e6 / us_d}
         except Exception as e:
             extras["direct_solver"] = {"error": repr(e)[:200]}
     cpu = None
@@ -616,24 +721,24 @@ def run_ours(args):
         line = {
             "metric": "linsys_solves_per_sec", "value": value, "unit": "solves/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "dtype": "f32", "data": data, "numerics": numerics_default,
             "pcg_iters_per_sec": tot_iters / (ms * 1e-3), "mean_iters_per_solve": tot_iters / (world * K),
+            "max_iter_exit_frac": float((fl_np != 0).mean()),
             "linsys_us": {"mean": float(win.mean()), "median": float(np.median(win)), "p95": float(np.percentile(win, 95)),
                           "what": "reference stopwatch window include/pcg/sqp.cuh:224-241 (sync, launch, 2 D2H, sync), "
                                   "device-resident inputs"},
-            "config": {"workload": "IIWA-size single trajectory: n=14, N=128, fp32, tol 1e-4, cap 167 "
-                                   "(BASELINE.json configs[1]); one solve per step",
-                       "ring": ring, "l2": f"ring of {ring} distinct systems = {ring * 2 * 3 * n * n * N * esz >> 20} MiB "
-                                           "> L2, so each step reads cold tiles",
-                       "multi_gpu": "replicas only (one trajectory stream per GPU); batched path in 'batched'"},
+            "config": workload_config(data, ring, host["source"]),
             "e2e": {"value": world * Ke / e2e_s, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "us_per_solve": 1e6 * e2e_s / Ke, "steps": Ke,
                     "api": "gbd_pcg_plan_solve_host_f32 (replaces solvePCG(h_S,...), interface.cuh:24-89)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": _ncu_traffic(), "peak_source": peak_src, "kernel": "gbd::pcg_cluster_kernel_v2<float,14,128,16,1>",
-                         "kernel_us": 1e6 * kernel_s, "bytes_per_iter": b_iter, "compulsory_gbs": compulsory,
+                         "traffic": _ncu_traffic(resolved["kernel"], resolved["cluster"]), "peak_source": peak_src,
+                         "kernel": f"{resolved['kernel']}<14,128,{resolved['cluster']}> (mode {resolved['mode']}, {resolved['threads']} threads x "
+                                   f"{resolved['cluster']} CTAs, read back from gbd_pcg_resolved_variant)",
+                         "kernel_us": 1e6 * kernel_s, "us_per_iter": 1e6 * kernel_s / max(1.0, it_np.mean()), "bytes_per_iter": b_iter,
+                         "compulsory_gbs": compulsory,
                          "note": "achieved is SpMV-equivalent bytes (tiles stay on-chip across iterations), not DRAM traffic; "
-                                 "this config is latency-bound by construction (0.6 MB working set)"},
+                                 "this config is latency-bound by construction (0.6 MB working set, one cluster-wide reduction per iteration)"},
             "clocks": clocks,
             "gpu_launches": int(launches_timed),
         }
@@ -659,6 +764,7 @@ def main():
     ap.add_argument("--no-batched", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the short legs for BASELINE.json configs 0, 2 and 4")
+    ap.add_argument("--no-refgpu", action="store_true", help="skip the reference GBD-PCG kernel legs (oracle/_ref)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--prewarm", type=float, default=0.5, help="seconds of untimed solves before the W warm-up steps")
     args = ap.parse_args()

@@ -16,6 +16,15 @@
 #include "gbd/gbd_cluster_pcg_v3.cuh"
 #include "gbd/gbd_cluster_pcg_v4.cuh"
 #include "gbd/gbd_cluster_pcg_v5.cuh"
+#include "gbd/gbd_cluster_pcg_fast.cuh"
+
+// Numerics of the drop-in pcg<T,n,N>.  Default (0): bit-identical to the reference kernel.  -DGBD_DROPIN_FAST=1: the tolerance-parity
+// kernel of gbd_cluster_pcg_fast.cuh (same contract, iteration count within +-2, lambda within 1e-3 relative: include/gbd_pcg.h)
+// for fp32 IIWA shapes N = 32 / 64 / 128, when the caller's block has enough threads -- build with -DPCG_NUM_THREADS=288
+// -DGBD_PCG_MAX_BLOCK=288 for N = 128 (160 threads suffice for N = 32 / 64); smaller blocks run the bit-exact body.
+#ifndef GBD_DROPIN_FAST
+#define GBD_DROPIN_FAST 0
+#endif
 
 #ifndef GBD_PCG_MAX_BLOCK
 #define GBD_PCG_MAX_BLOCK 256           // upper bound on the caller's block size (register budget of pcg<>)
@@ -56,6 +65,21 @@ constexpr size_t fast4_smem(size_t n, size_t N)
     const size_t xs = (n + 3) / 4 * 4;
     return 16 + 8 * (3 * N + 8 * xs) + 2 * a16(4 * 10 * xs) + 2 * a16(4 * 8 * 3 * n * n);
 }
+// tolerance-parity body (GBD_DROPIN_FAST): CTAs per system for the shapes it is built for, 0 = not available
+constexpr size_t fastcg_cluster(size_t n, size_t N, size_t e)
+{
+#ifdef GBD_DROPIN_NO_CLUSTER
+    return 0;
+#else
+    return (GBD_DROPIN_FAST && e == 4 && n % 2 == 0 && n <= 16) ? (N == 32 ? 4 : ((N == 64 || N == 128) ? 8 : 0)) : 0;
+#endif
+}
+constexpr size_t fastcg_threads(size_t n, size_t N, size_t e) { return fastcg_cluster(n, N, e) ? (N / fastcg_cluster(n, N, e) + 2) * 16 : 0; }
+constexpr size_t fastcg_smem(size_t n, size_t N, size_t e)
+{
+    const size_t C = fastcg_cluster(n, N, e), R = C ? N / C : 0;
+    return C ? 32 + 2 * C * 16 + R * 16 * 8 + 2 * (2 * 2 * 16) * 8 + 4 * ((R + 6) + (R + 4) + (R + 2)) * 16 + 4 * ((R + 4) + (R + 2)) * 3 * n * n : 0;
+}
 constexpr bool fast_shape(size_t n, size_t N, size_t e)
 {
 #ifdef GBD_DROPIN_NO_CLUSTER
@@ -80,9 +104,17 @@ constexpr size_t grid_rows(size_t n, size_t N, size_t e)     // knot rows per CT
 //         RG = 8 when the block has >= 8 row groups of threads, else 1.  CTAs beyond N/RG return.
 template <typename T, uint32_t n, uint32_t N>
 struct Shape {
-    static constexpr bool FAST = fast_shape(n, N, sizeof(T));
-    static constexpr bool FAST4 = fast4_shape(n, N, sizeof(T));
-    static constexpr uint32_t C = FAST4 ? N / 8 : (FAST ? N / 16 : 1);
+    static constexpr uint32_t CCG = (uint32_t)fastcg_cluster(n, N, sizeof(T));
+    static constexpr bool FASTCG = CCG != 0;
+    static constexpr bool FAST = !FASTCG && fast_shape(n, N, sizeof(T));
+    static constexpr bool FAST4 = !FASTCG && fast4_shape(n, N, sizeof(T));
+    static constexpr uint32_t C = FASTCG ? CCG : (FAST4 ? N / 8 : (FAST ? N / 16 : 1));
+    using FastCg = gbd::ClusterPcgFast<FASTCG ? n : 2, FASTCG ? N : 8, FASTCG ? CCG : 2>;
+    static constexpr uint32_t NT_FASTCG = FASTCG ? FastCg::NT : 0;
+    static_assert(!FASTCG || (FastCg::SMEM_BYTES == fastcg_smem(n, N, sizeof(T)) && FastCg::NT == fastcg_threads(n, N, sizeof(T))), "run-time smem formula out of sync");
+    // FASTCG fallback for blocks that are too small: the packet body (FAST4-style cluster of the same size does not exist for every
+    // shape), so the grid body serves them; it needs no cluster and ignores the compile-time cluster dimensions
+    static constexpr bool FASTCG_ONLY = FASTCG;
     static constexpr uint32_t NT_FAST = 128;
     // co-residency of all N CTAs (cooperative launch): beyond 2 x 148 CTAs the register budget must allow 4 blocks of
     // 128 threads (= 2 of GBD_PCG_MAX_BLOCK) per SM
@@ -100,7 +132,8 @@ struct Shape {
     static_assert(gbd::GridPcg<T, n, N, 1>::SMEM_BYTES == grid_smem(n, N, 1, sizeof(T)), "run-time smem formula out of sync");
     static constexpr size_t SMEM_G1 = gbd::GridPcg<T, n, N, 1>::SMEM_BYTES;
     static constexpr size_t SMEM_GR = gbd::GridPcg<T, n, N, RG>::SMEM_BYTES;
-    static constexpr size_t SMEM_BYTES = SMEM_FAST > (SMEM_G1 > SMEM_GR ? SMEM_G1 : SMEM_GR) ? SMEM_FAST : (SMEM_G1 > SMEM_GR ? SMEM_G1 : SMEM_GR);
+    static constexpr size_t SMEM_BASE = SMEM_FAST > (SMEM_G1 > SMEM_GR ? SMEM_G1 : SMEM_GR) ? SMEM_FAST : (SMEM_G1 > SMEM_GR ? SMEM_G1 : SMEM_GR);
+    static constexpr size_t SMEM_BYTES = (FASTCG && FastCg::SMEM_BYTES > SMEM_BASE) ? FastCg::SMEM_BYTES : SMEM_BASE;
 };
 // packet workspace + epoch counter of one instantiation (zero-initialised by the loader); R = 1 is the largest layout
 template <typename T, uint32_t n, uint32_t N>
@@ -119,6 +152,19 @@ pcg(T *d_S, T *d_Pinv, T *d_gamma, T *d_lambda, T *d_r, T *d_p, T *d_v_temp, T *
     extern __shared__ __align__(16) unsigned char gbd_dropin_smem[];
     (void)d_v_temp; (void)d_eta_new_temp;          // reference scratch for its smem trees; not needed here
     uint8_t *d_flag = reinterpret_cast<uint8_t *>(d_max_iter_exit);
+    if constexpr (SH::FASTCG) {
+        if (blockDim.x >= SH::NT_FASTCG) {
+            if (gbd::cluster_idx() != 0) return;                  // whole clusters leave together
+            const uint32_t tma = ((((uintptr_t)d_S) | ((uintptr_t)d_Pinv)) & 15u) == 0 ? 1u : 0u;
+            gbd::PcgArgs<float> a{d_S, d_Pinv, d_gamma, d_lambda, d_r, d_p, d_iters, d_flag, 1u, max_iter, exit_tol, tma};
+            gbd::pcg_cluster_fast_init<state_size, knot_points, SH::CCG>(gbd_dropin_smem);
+            __syncthreads();
+            gbd::cluster_sync();
+            if (threadIdx.x < SH::NT_FASTCG) gbd::pcg_cluster_fast_run<state_size, knot_points, SH::CCG, false, false>(a, gbd_dropin_smem, 0u, 1u);
+            gbd::cluster_sync();
+            return;
+        }
+    }
     if constexpr (SH::FAST4) {
         if (blockDim.x >= SH::NT_FAST) {
             if (gbd::cluster_idx() != 0) return;                  // whole clusters leave together
@@ -181,6 +227,7 @@ size_t pcgSharedMemSize(uint32_t state_size, uint32_t knot_points)
     if (gbd_dropin::fast_shape(n, N, e) && gbd_dropin::fast5_shape(N) && gbd_dropin::fast5_smem(n, N) > need) need = gbd_dropin::fast5_smem(n, N);
     const size_t rg = gbd_dropin::grid_rows(n, N, e);
     if (rg > 1 && gbd_dropin::grid_smem(n, N, rg, e) > need) need = gbd_dropin::grid_smem(n, N, rg, e);
+    if (gbd_dropin::fastcg_smem(n, N, e) > need) need = gbd_dropin::fastcg_smem(n, N, e);
     return need;
 }
 

@@ -57,9 +57,9 @@ const Pref g_prefs[] = {
     {14, 128, true, false, 16, 20},  {14, 128, true, false, 8, 20},   {14, 32, true, false, 4, 20},
     {14, 64, true, false, 8, 20},    {14, 256, true, false, 16, 20},
     // tolerance parity, batched: the single-solve fast kernels keep one system per 8-16 SMs and lose to the bit-exact v5 kernel
-    // on throughput (131 K vs 210 K systems/s at 1024 x N = 128, profiles/r02_ab_batched.log), so batches of these shapes
+    // on throughput (131 K vs 210 K systems/s at 1024 x N = 128, 1.1 M vs 1.7 M at N = 32, profiles/r02_ab_batched.log), so batches of these shapes
     // stay on v5 until a batched fast kernel is listed here
-    {14, 128, true, true, 4, 11},    {14, 32, true, true, 2, 20},     {14, 32, true, true, 2, 11},
+    {14, 128, true, true, 4, 11},    {14, 32, true, true, 2, 11},
 };
 
 struct Tuning { uint32_t n, N; bool f64; uint32_t C; int mode; };
