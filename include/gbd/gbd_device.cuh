@@ -16,6 +16,41 @@ namespace gbd {
 // ----------------------------------------------------------------------------- addressing
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// ---- shared memory through explicit 32-bit addresses.  Measured (profiles/r02_timeline_fastb.log): with many live registers the
+// compiler does not keep shared-memory base addresses in registers, it re-derives them -- S2UR SR_CgaCtaId for every block of
+// accesses through a C++ pointer, S2R SR_SWINHI for every store into a peer's shared memory -- and these special-register reads
+// cost 50-100 cycles each on the dependent chain of an iteration.  The hot loops therefore hold ONE opaque base address and go
+// through these accessors; peers' shared memory is addressed through generic pointers formed once (cluster_generic).
+__device__ __forceinline__ uint32_t opaque(uint32_t x) { asm volatile("" : "+r"(x)); return x; }
+__device__ __forceinline__ uint64_t opaque(uint64_t x) { asm volatile("" : "+l"(x)); return x; }
+__device__ __forceinline__ float lds_f32(uint32_t a)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ float2 lds_f32x2(uint32_t a)
+{
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 lds_f32x4(uint32_t a)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_f32x2(uint32_t a, float x, float y) { asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(x), "f"(y) : "memory"); }
+// generic address of a shared::cluster address (own or a peer's shared memory), for stores that would otherwise read SR_SWINHI
+__device__ __forceinline__ uint64_t cluster_generic(uint32_t cluster_addr)
+{
+    uint64_t g;
+    asm volatile("cvta.shared::cluster.u64 %0, %1;" : "=l"(g) : "l"((uint64_t)cluster_addr));
+    return g;
+}
+
 __device__ __forceinline__ uint32_t cluster_ctarank()
 {
     uint32_t r;

@@ -20,14 +20,20 @@
 
 // Numerics of the drop-in pcg<T,n,N>.  Default (0): bit-identical to the reference kernel.  -DGBD_DROPIN_FAST=1: the tolerance-parity
 // kernel of gbd_cluster_pcg_fast.cuh (same contract, iteration count within +-2, lambda within 1e-3 relative: include/gbd_pcg.h)
-// for fp32 IIWA shapes N = 32 / 64 / 128, when the caller's block has enough threads -- build with -DPCG_NUM_THREADS=288
-// -DGBD_PCG_MAX_BLOCK=288 for N = 128 (160 threads suffice for N = 32 / 64); smaller blocks run the bit-exact body.
+// for fp32 IIWA shapes N = 32 / 64 / 128 (clusters of N/8 CTAs, 8 knot rows each), when the caller's block has at least 160
+// threads -- build with -DPCG_NUM_THREADS=160 (GBD_PCG_MAX_BLOCK then defaults to 160); smaller blocks run the bit-exact body.
+// N = 128 uses 16-CTA clusters, a non-portable size: call checkPcgOccupancy first (examples/track_iiwa_pcg.cu:24 does), it
+// sets cudaFuncAttributeNonPortableClusterSizeAllowed on the kernel.
 #ifndef GBD_DROPIN_FAST
 #define GBD_DROPIN_FAST 0
 #endif
 
 #ifndef GBD_PCG_MAX_BLOCK
+#if GBD_DROPIN_FAST
+#define GBD_PCG_MAX_BLOCK 160           // the tolerance-parity body wants its registers: 160 threads, two blocks per SM
+#else
 #define GBD_PCG_MAX_BLOCK 256           // upper bound on the caller's block size (register budget of pcg<>)
+#endif
 #endif
 
 namespace gbd_dropin {
@@ -71,7 +77,7 @@ constexpr size_t fastcg_cluster(size_t n, size_t N, size_t e)
 #ifdef GBD_DROPIN_NO_CLUSTER
     return 0;
 #else
-    return (GBD_DROPIN_FAST && e == 4 && n % 2 == 0 && n <= 16) ? (N == 32 ? 4 : ((N == 64 || N == 128) ? 8 : 0)) : 0;
+    return (GBD_DROPIN_FAST && e == 4 && n % 2 == 0 && n <= 16 && (N == 32 || N == 64 || N == 128)) ? N / 8 : 0;
 #endif
 }
 constexpr size_t fastcg_threads(size_t n, size_t N, size_t e) { return fastcg_cluster(n, N, e) ? (N / fastcg_cluster(n, N, e) + 2) * 16 : 0; }
@@ -112,13 +118,12 @@ struct Shape {
     using FastCg = gbd::ClusterPcgFast<FASTCG ? n : 2, FASTCG ? N : 8, FASTCG ? CCG : 2>;
     static constexpr uint32_t NT_FASTCG = FASTCG ? FastCg::NT : 0;
     static_assert(!FASTCG || (FastCg::SMEM_BYTES == fastcg_smem(n, N, sizeof(T)) && FastCg::NT == fastcg_threads(n, N, sizeof(T))), "run-time smem formula out of sync");
-    // FASTCG fallback for blocks that are too small: the packet body (FAST4-style cluster of the same size does not exist for every
-    // shape), so the grid body serves them; it needs no cluster and ignores the compile-time cluster dimensions
-    static constexpr bool FASTCG_ONLY = FASTCG;
+    // FASTCG with a block that is too small: the grid body serves it (it needs no cluster and ignores the cluster dimensions)
     static constexpr uint32_t NT_FAST = 128;
     // co-residency of all N CTAs (cooperative launch): beyond 2 x 148 CTAs the register budget must allow 4 blocks of
     // 128 threads (= 2 of GBD_PCG_MAX_BLOCK) per SM
-    static constexpr uint32_t MIN_BLOCKS = N > 296 ? 2 : 1;
+    // (tolerance-parity body: 16-CTA clusters of 160 threads; two blocks per SM make all N = 128 CTAs co-resident)
+    static constexpr uint32_t MIN_BLOCKS = (N > 296 || FASTCG) ? 2 : 1;
     static constexpr uint32_t G = n <= 16 ? 16 : (n <= 32 ? 32 : (n + 31) / 32 * 32);
     static constexpr uint32_t RG = (uint32_t)grid_rows(n, N, sizeof(T));
     using Fast = gbd::ClusterPcg3<FAST ? n : 2, FAST ? N : 16, FAST ? C : 1, false>;
@@ -231,6 +236,9 @@ size_t pcgSharedMemSize(uint32_t state_size, uint32_t knot_points)
     return need;
 }
 
+// Replaces checkPcgOccupancy (pcg.cuh:23-49), same contract: prints the reference's messages and exits with its codes (5: no
+// cooperative launch, 6: the N CTAs of the reference's launch cannot be co-resident), returns true otherwise.  Also opts the kernel
+// in to what its bodies need (shared memory beyond 48 KB, 16-CTA clusters), so the reference's launch site needs no change.
 template <typename T>
 bool checkPcgOccupancy(void *kernel, dim3 block, uint32_t state_size, uint32_t knot_points)
 {
@@ -241,14 +249,30 @@ bool checkPcgOccupancy(void *kernel, dim3 block, uint32_t state_size, uint32_t k
     gpuErrchk(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     if (!coop) {
         printf("[Error] Device does not support Cooperative Threads\n");
-        return false;
+        exit(5);
     }
     if (smem > 48 * 1024) gpuErrchk(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gpuErrchk(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, (int)(block.x * block.y * block.z), smem));
-    if ((int)knot_points > sms * per_sm) {
-        printf("Too many knot points ([%d]). Device supports [%d] active blocks, over [%d] SMs.\n", knot_points,
-               sms * per_sm, sms);
-        return false;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) (void)cudaGetLastError();
+    const int threads = (int)(block.x * block.y * block.z);
+    gpuErrchk(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+    int capacity = sms * per_sm;
+    // kernels with compile-time cluster dimensions: whole clusters must be placed, which can be fewer CTAs than sms * per_sm
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(knot_points);
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    int clusters = 0;
+    cudaFuncAttributes fa;
+    if (cudaOccupancyMaxActiveClusters(&clusters, kernel, &cfg) == cudaSuccess && cudaFuncGetAttributes(&fa, kernel) == cudaSuccess &&
+        fa.clusterDimMustBeSet == 0 && fa.requiredClusterWidth > 0) {
+        const int by_cluster = clusters * fa.requiredClusterWidth;
+        if (by_cluster < capacity) capacity = by_cluster;
+    } else {
+        (void)cudaGetLastError();
+    }
+    if ((int)knot_points > capacity) {
+        printf("Too many knot points ([%d]). Device supports [%d] active blocks, over [%d] SMs.\n", knot_points, capacity, sms);
+        exit(6);
     }
     return true;
 }

@@ -34,6 +34,7 @@ std::vector<Variant> &variants()
         gbdlib::register_exact_v1v2(t);
         gbdlib::register_exact_v3v5(t);
         gbdlib::register_fast(t);
+        gbdlib::register_fastb(t);
         gbdlib::register_grid(t);
         return t;
     }();
@@ -56,9 +57,11 @@ const Pref g_prefs[] = {
     // tolerance parity, single solve
     {14, 128, true, false, 16, 20},  {14, 128, true, false, 8, 20},   {14, 32, true, false, 4, 20},
     {14, 64, true, false, 8, 20},    {14, 256, true, false, 16, 20},
-    // tolerance parity, batched: the single-solve fast kernels keep one system per 8-16 SMs and lose to the bit-exact v5 kernel
-    // on throughput (131 K vs 210 K systems/s at 1024 x N = 128, 1.1 M vs 1.7 M at N = 32, profiles/r02_ab_batched.log), so batches of these shapes
-    // stay on v5 until a batched fast kernel is listed here
+    // tolerance parity, batched: the packed-row kernels (few CTAs per system, 16-32 knot rows each: many systems in flight), then
+    // the bit-exact v5 kernel (the single-solve fast kernels keep one system per 8-16 SMs and lose to it on throughput:
+    // 131 K vs 210 K systems/s at 1024 x N = 128, profiles/r02_ab_batched.log)
+    {14, 128, true, true, 4, 27},    {14, 32, true, true, 1, 27},     {14, 64, true, true, 2, 27},
+    {14, 256, true, true, 8, 27},    {14, 512, true, true, 16, 27},
     {14, 128, true, true, 4, 11},    {14, 32, true, true, 2, 11},
 };
 
@@ -146,7 +149,8 @@ Variant *find_variant(uint32_t n, uint32_t N, bool f64, bool batched)
         Variant *grid = nullptr;
         for (auto &v : variants()) {
             if (v.n != n || v.N != N || v.f64 != f64 || v.unusable || mode_is_fast(v.mode) != want_fast) continue;
-            if (v.mode == 10 || v.mode == 14 || v.mode == gbdlib::MODE_FAST_PROF) continue;      // timeline builds are never a default
+            if (v.mode == 10 || v.mode == 14 || v.mode == gbdlib::MODE_FAST_PROF || v.mode == gbdlib::MODE_FAST_B_PROF) continue;      // timeline builds are never a default
+            if (gbdlib::mode_is_packed(v.mode)) continue;                                       // batch kernels: only by preference
             if (mode_is_grid(v.mode)) { if (!grid) grid = &v; continue; }                          // whole-GPU kernels last
             return &v;
         }

@@ -20,8 +20,12 @@ namespace gbdlib {
 //   tolerance-parity family (GBD_PCG_NUMERICS_FAST; include/gbd/gbd_cluster_pcg_fast.cuh):
 //      20 = fast cluster kernel (single-exchange recurrence, per-CTA reductions), 1 CTA/SM; 21 = 2 CTAs/SM budget;
 //      22 = its timeline build; 24 = fast grid kernel (n = 64: whole GPU on one system)
-//      26 = fast batched kernel (one system per CTA pair, Pinv rows in shared memory)
-constexpr int MODE_GRID = 4, MODE_FAST = 20, MODE_FAST2 = 21, MODE_FAST_PROF = 22, MODE_FAST_GRID = 24, MODE_FAST_BATCH = 26;
+//      26 = fast cluster kernel with packed knot rows (n lanes per row, 16 or 32 rows per CTA): the batch kernels
+//      27 = fast batch kernel (gbd_cluster_pcg_fastb.cuh: four rows of one matrix per thread, P-threads / S-threads), 1 CTA/SM;
+//      28 = the same, 2 CTAs/SM; 29 = its timeline build
+constexpr int MODE_GRID = 4, MODE_FAST = 20, MODE_FAST2 = 21, MODE_FAST_PROF = 22, MODE_FAST_GRID = 24, MODE_FAST_BATCH = 26,
+              MODE_FAST_B = 27, MODE_FAST_B2 = 28, MODE_FAST_B_PROF = 29;
+inline bool mode_is_packed(int mode) { return mode >= 26 && mode <= 28; }   // per-CTA products parked n per knot row (oracle: lanes = n)
 inline bool mode_is_fast(int mode) { return mode >= 20; }
 inline bool mode_is_grid(int mode) { return mode == MODE_GRID || mode == MODE_FAST_GRID; }
 
@@ -44,5 +48,6 @@ void register_exact_v3v5(std::vector<Variant> &v);
 void register_exact_v4(std::vector<Variant> &v);
 void register_grid(std::vector<Variant> &v);
 void register_fast(std::vector<Variant> &v);
+void register_fastb(std::vector<Variant> &v);
 
 }  // namespace gbdlib

@@ -12,6 +12,15 @@ static Variant make_fast()
     return Variant{n, N, C, PROF ? MODE_FAST_PROF : (MINB == 1 ? MODE_FAST : MODE_FAST2), false, K::NT, K::SMEM_BYTES,
                    (const void *)pcg_cluster_kernel_fast<n, N, C, MINB, PROF>, "gbd::pcg_cluster_kernel_fast"};
 }
+// batch kernels: knot rows packed n lanes each (no idle lanes), 16 or 32 knot rows per CTA -- few CTAs per system, so many
+// systems in flight; for n = 14 and 32 rows a CTA is 15 warps, at most 4 per scheduler partition = 128 registers per thread
+template <uint32_t n, uint32_t N, uint32_t C>
+static Variant make_fast_packed()
+{
+    using K = ClusterPcgFast<n, N, C, n>;
+    return Variant{n, N, C, MODE_FAST_BATCH, false, K::NT, K::SMEM_BYTES,
+                   (const void *)pcg_cluster_kernel_fast<n, N, C, 1, false, n>, "gbd::pcg_cluster_kernel_fast(packed)"};
+}
 
 void register_fast(std::vector<Variant> &v)
 {
@@ -21,6 +30,8 @@ void register_fast(std::vector<Variant> &v)
         make_fast<14, 256, 16, 1>(),  make_fast<14, 16, 4, 1>(),    make_fast<14, 8, 2, 1>(),
         make_fast<6, 12, 3, 1>(),     make_fast<6, 12, 2, 1>(),
         make_fast<14, 128, 16, 1, true>(), make_fast<14, 128, 8, 1, true>(), make_fast<14, 32, 4, 1, true>(),
+        make_fast_packed<14, 128, 4>(), make_fast_packed<14, 128, 8>(), make_fast_packed<14, 64, 2>(), make_fast_packed<14, 32, 1>(),
+        make_fast_packed<14, 32, 2>(),  make_fast_packed<14, 256, 8>(), make_fast_packed<14, 512, 16>(),
     };
     for (const Variant &x : list) v.push_back(x);
 }

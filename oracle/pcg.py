@@ -117,15 +117,17 @@ def fast_lib():
             subprocess.check_call(["make", "-s", "-C", _HERE, "oracle"])
         _fast = C.CDLL(_FAST_PATH)
         f32p = C.POINTER(C.c_float)
-        _fast.pcg_fast_oracle_f32.restype = C.c_int
-        _fast.pcg_fast_oracle_f32.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, f32p, f32p, f32p, f32p, C.c_uint32, C.c_float,
-                                              C.POINTER(C.c_uint32), C.POINTER(C.c_uint8), f32p, f32p, f32p]
+        _fast.pcg_fast_oracle_g_f32.restype = C.c_int
+        _fast.pcg_fast_oracle_g_f32.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, f32p, f32p, f32p, f32p, C.c_uint32, C.c_float,
+                                                C.POINTER(C.c_uint32), C.POINTER(C.c_uint8), f32p, f32p, f32p]
     return _fast
 
 
-def pcg_fast(S, Pinv, gamma, lambda0, n: int, N: int, cluster: int, max_iter: int, exit_tol: float):
-    """The fast kernels' arithmetic (Chronopoulos-Gear recurrence, per-CTA reductions for a cluster of `cluster` CTAs),
-    include/gbd/gbd_cluster_pcg_fast.cuh.  Same return dict as pcg()."""
+def pcg_fast(S, Pinv, gamma, lambda0, n: int, N: int, cluster: int, max_iter: int, exit_tol: float, lanes: int = 16):
+    """The fast kernels' arithmetic (Chronopoulos-Gear recurrence, per-CTA reductions for a cluster of `cluster` CTAs whose knot
+    rows occupy `lanes` lanes each: 16, or n for the packed kernels; 0 = the reduction order of the batch kernel
+    include/gbd/gbd_cluster_pcg_fastb.cuh), include/gbd/gbd_cluster_pcg_fast.cuh.
+    Same return dict as pcg()."""
     S = np.ascontiguousarray(S, np.float32).reshape(-1)
     Pinv = np.ascontiguousarray(Pinv, np.float32).reshape(-1)
     gamma = np.ascontiguousarray(gamma, np.float32).reshape(-1)
@@ -134,9 +136,9 @@ def pcg_fast(S, Pinv, gamma, lambda0, n: int, N: int, cluster: int, max_iter: in
     r = np.empty(n * N, np.float32)
     p = np.empty(n * N, np.float32)
     iters, flag, eta = C.c_uint32(0), C.c_uint8(0), C.c_float(0)
-    rc = fast_lib().pcg_fast_oracle_f32(n, N, cluster, _p(S, C.c_float), _p(Pinv, C.c_float), _p(gamma, C.c_float),
-                                        _p(lam, C.c_float), max_iter, exit_tol, C.byref(iters), C.byref(flag),
-                                        _p(r, C.c_float), _p(p, C.c_float), C.byref(eta))
+    rc = fast_lib().pcg_fast_oracle_g_f32(n, N, cluster, lanes, _p(S, C.c_float), _p(Pinv, C.c_float), _p(gamma, C.c_float),
+                                          _p(lam, C.c_float), max_iter, exit_tol, C.byref(iters), C.byref(flag),
+                                          _p(r, C.c_float), _p(p, C.c_float), C.byref(eta))
     if rc:
         raise ValueError(f"pcg_fast_oracle rc={rc}")
     return dict(lam=lam, iters=int(iters.value), max_iter_exit=bool(flag.value), r=r, p=p, eta=float(eta.value))

@@ -15,10 +15,10 @@
  *               first term a product, then one FMA per column, ascending), combined as
  *               ((L.lo + D.lo) + R.lo) + ((L.hi + D.hi) + R.hi); pad tiles and rows outside the system
  *               contribute exact zeros
- *   dots        per CTA of R = N/C own knot rows laid out in 16-lane groups: the 16 R per-thread products are
- *               added by eight lanes, lane l taking the products {16m + 2l, 16m + 2l + 1} and then a balanced
- *               tree over m, then an XOR butterfly 4,2,1 over the eight; the C CTA partials are summed in a
- *               balanced tree in ascending CTA order
+ *   dots        per CTA of R = N/C own knot rows laid out in groups of G lanes (G = 16, lanes n .. 15 idle, or G = n,
+ *               packed): the G R per-thread products are added by LN lanes (8, or 16 when G R >= 384), lane l taking
+ *               the products {2 LN m + 2l, 2 LN m + 2l + 1} and then a balanced tree over m, then an XOR butterfly
+ *               LN/2 .. 1 over the LN lanes; the C CTA partials are summed in a balanced tree in ascending CTA order
  *   scalars     correctly rounded reciprocals (1.0f/x) times products, FMAs as written
  *
  * Layout as in pcg_oracle.c: S, Pinv = [N][3][n][n], column-major tiles, tiles (0,left), (N-1,right) unused.
@@ -72,33 +72,66 @@ static float tree_sum(float *v, uint32_t cnt)
     return v[0];
 }
 
-/* the kernels' reduction of per-element products a[i]*b[i] (i over N*n) for cluster size C */
-static float dot_fast(uint32_t n, uint32_t N, uint32_t C, const float *a, const float *b)
+/* the batch kernel's reduction (gbd_cluster_pcg_fastb.cuh): four lanes per knot row, lane q holding the elements q, q + n/2, q + 4,
+ * q + 4 + n/2 (those that exist); a lane adds its products as (p0 + p1) + (p2 + p3), missing ones as +0; a warp = eight knot rows
+ * = 32 lanes adds them in an XOR butterfly 1, 2, 4, 8, 16 (a balanced tree in lane order); the R/8 warp sums of a CTA and then the
+ * C CTA sums are added in balanced trees in ascending order */
+static float dot_fast_b(uint32_t n, uint32_t N, uint32_t C, const float *a, const float *b)
 {
-    const uint32_t R = N / C, NOWN = R * 16, PPL = NOWN / 16;
+    const uint32_t R = N / C, H = n / 2, W = R / 8;
+    float part[16];
+    for (uint32_t cr = 0; cr < C; cr++) {
+        float wsum[128];
+        for (uint32_t w = 0; w < W; w++) {
+            float lanev[32];
+            for (uint32_t l = 0; l < 32; l++) {
+                const uint32_t g = w * 8 + l / 4, q = l % 4;
+                const uint32_t e[4] = {q, q + H, q + 4, q + 4 + H};
+                const int ok[4] = {q < H, q < H, q + 4 < H, q + 4 < H};
+                float p[4];
+                for (int k = 0; k < 4; k++) {
+                    const size_t i = ((size_t)cr * R + g) * n + e[k];
+                    p[k] = ok[k] ? a[i] * b[i] : 0.0f;
+                }
+                lanev[l] = (p[0] + p[1]) + (p[2] + p[3]);
+            }
+            wsum[w] = tree_sum(lanev, 32);
+        }
+        part[cr] = tree_sum(wsum, W);
+    }
+    return tree_sum(part, C);
+}
+
+/* the kernels' reduction of per-element products a[i]*b[i] (i over N*n) for cluster size C and G lanes per knot row
+ * (G = 0: the batch kernel's order, above) */
+static float dot_fast(uint32_t n, uint32_t N, uint32_t C, uint32_t G, const float *a, const float *b)
+{
+    if (G == 0) return dot_fast_b(n, N, C, a, b);
+    const uint32_t R = N / C, NOWN = R * G, LN = NOWN >= 384 ? 16 : 8, PPL = NOWN / (2 * LN);
     float part[16];
     float *prod = (float *)malloc(NOWN * sizeof(float));
+    float *v = (float *)malloc(PPL * sizeof(float));
     for (uint32_t cr = 0; cr < C; cr++) {
-        /* thread t = 16 g + j of the own-row warps parks its product; idle lanes j >= n hold zeros */
+        /* thread t = G g + j of the own-row warps parks its product; idle lanes j >= n hold zeros */
         for (uint32_t t = 0; t < NOWN; t++) {
-            const uint32_t g = t / 16, j = t % 16;
+            const uint32_t g = t / G, j = t % G;
             const size_t i = ((size_t)cr * R + g) * n + j;
             prod[t] = j < n ? a[i] * b[i] : 0.0f;
         }
-        /* eight lanes: lane l adds the products {16 m + 2 l, 16 m + 2 l + 1}, m < PPL, then a balanced tree over m */
-        float lanev[8];
-        for (uint32_t l = 0; l < 8; l++) {
-            float v[128];
-            for (uint32_t m = 0; m < PPL; m++) v[m] = prod[16 * m + 2 * l] + prod[16 * m + 2 * l + 1];
+        /* LN lanes: lane l adds the products {2 LN m + 2 l, 2 LN m + 2 l + 1}, m < PPL, then a balanced tree over m */
+        float lanev[16];
+        for (uint32_t l = 0; l < LN; l++) {
+            for (uint32_t m = 0; m < PPL; m++) v[m] = prod[2 * LN * m + 2 * l] + prod[2 * LN * m + 2 * l + 1];
             lanev[l] = tree_sum(v, PPL);
         }
-        for (uint32_t s = 4; s >= 1; s >>= 1) {
-            float nv[8];
-            for (uint32_t l = 0; l < 8; l++) nv[l] = lanev[l] + lanev[l ^ s];
+        for (uint32_t s = LN / 2; s >= 1; s >>= 1) {
+            float nv[16];
+            for (uint32_t l = 0; l < LN; l++) nv[l] = lanev[l] + lanev[l ^ s];
             memcpy(lanev, nv, sizeof nv);
         }
         part[cr] = lanev[0];
     }
+    free(v);
     free(prod);
     return tree_sum(part, C);       /* every lane of the gathering warp adds the C pairs in the same balanced tree */
 }
@@ -107,12 +140,12 @@ static float dot_fast(uint32_t n, uint32_t N, uint32_t C, const float *a, const 
  * Returns 0, or -1 on bad arguments.  lambda is in/out; r_out / p_out (nullable) receive the final residual and
  * direction; eta_out (nullable) the last gamma = r.Pinv r.
  */
-ORACLE_API int pcg_fast_oracle_f32(uint32_t n, uint32_t N, uint32_t C, const float *S, const float *Pinv, const float *gamma,
-                                   float *lambda, uint32_t max_iter, float exit_tol, uint32_t *iters_out,
-                                   uint8_t *max_iter_exit_out, float *r_out, float *p_out, float *eta_out)
+ORACLE_API int pcg_fast_oracle_g_f32(uint32_t n, uint32_t N, uint32_t C, uint32_t G, const float *S, const float *Pinv, const float *gamma,
+                                     float *lambda, uint32_t max_iter, float exit_tol, uint32_t *iters_out,
+                                     uint8_t *max_iter_exit_out, float *r_out, float *p_out, float *eta_out)
 {
     if (!S || !Pinv || !gamma || !lambda || n < 2 || n > 16 || C < 1 || C > 16 || N % C || N / C < 2) return -1;
-    if (n % 2 || (N / C) % 2) return -1;
+    if (n % 2 || (N / C) % 2 || (G != 16 && G != n && G != 0) || (G && ((N / C) * G) % 16) || (!G && (N / C) % 8)) return -1;
     const size_t len = (size_t)n * N;
     float *buf = (float *)calloc(7 * len, sizeof(float));
     if (!buf) return -1;
@@ -122,7 +155,7 @@ ORACLE_API int pcg_fast_oracle_f32(uint32_t n, uint32_t N, uint32_t C, const flo
     for (size_t i = 0; i < len; i++) r[i] = gamma[i] - t[i];
     band(n, N, Pinv, r, u);
     band(n, N, S, u, w);
-    float gam = dot_fast(n, N, C, r, u), del = dot_fast(n, N, C, w, u);
+    float gam = dot_fast(n, N, C, G, r, u), del = dot_fast(n, N, C, G, w, u);
     float alpha = gam * (1.0f / del), beta = 0.0f;
     float rgam = 1.0f / gam, q = del * rgam;
     uint32_t iter = 0;
@@ -136,7 +169,7 @@ ORACLE_API int pcg_fast_oracle_f32(uint32_t n, uint32_t N, uint32_t C, const flo
         }
         band(n, N, Pinv, r, u);
         band(n, N, S, u, w);
-        const float gam_new = dot_fast(n, N, C, r, u), del_new = dot_fast(n, N, C, w, u);
+        const float gam_new = dot_fast(n, N, C, G, r, u), del_new = dot_fast(n, N, C, G, w, u);
         gam = gam_new;
         if (fabsf(gam_new) < exit_tol) { iter++; flag = 0; break; }
         beta = gam_new * rgam;
@@ -153,4 +186,12 @@ ORACLE_API int pcg_fast_oracle_f32(uint32_t n, uint32_t N, uint32_t C, const flo
     if (eta_out) *eta_out = gam;
     free(buf);
     return 0;
+}
+
+/* the 16-lanes-per-row kernels (single solves) */
+ORACLE_API int pcg_fast_oracle_f32(uint32_t n, uint32_t N, uint32_t C, const float *S, const float *Pinv, const float *gamma,
+                                   float *lambda, uint32_t max_iter, float exit_tol, uint32_t *iters_out,
+                                   uint8_t *max_iter_exit_out, float *r_out, float *p_out, float *eta_out)
+{
+    return pcg_fast_oracle_g_f32(n, N, C, 16, S, Pinv, gamma, lambda, max_iter, exit_tol, iters_out, max_iter_exit_out, r_out, p_out, eta_out);
 }

@@ -15,10 +15,11 @@ def test_fast_order_within_tolerance_of_reference_kernel(oracle_pcg, path):
     n, N = g["n"], g["N"]
     for run in g["runs"]:
         r_ref = oracle_pcg.rel_residual(g["S"], g["gamma"], run["lam"], n, N)
-        for C in (4, 8, 16):
-            if N // C < 2:
+        # (cluster size, lanes per knot row): the single-solve shapes, then the packed batch shapes (32 knot rows per CTA)
+        for C, lanes in ((4, 16), (8, 16), (16, 16), (N // 32, n)):
+            if C < 1 or N // C < 2:
                 continue
-            f = oracle_pcg.pcg_fast(g["S"], g["Pinv"], g["gamma"], np.zeros(n * N, np.float32), n, N, C, run["cap"], run["tol"])
+            f = oracle_pcg.pcg_fast(g["S"], g["Pinv"], g["gamma"], np.zeros(n * N, np.float32), n, N, C, run["cap"], run["tol"], lanes=lanes)
             assert abs(f["iters"] - run["iters"]) <= 2
             if run["iters"] < run["cap"] - 2 or run["max_iter_exit"]:
                 assert f["max_iter_exit"] == run["max_iter_exit"]

@@ -94,9 +94,10 @@ def test_every_fast_variant_bit_exact_vs_its_own_oracle(torch_cuda, capi, oracle
     L = capi.lib()
     seen = 0
     for v in capi.variants():
-        if not v["fast"] or v["mode"] not in (20, 21):
+        if not v["fast"] or v["mode"] not in (20, 21, 26, 27, 28):
             continue
         n, N, C = v["n"], v["N"], v["cluster"]
+        lanes = {26: n, 27: 0, 28: 0}.get(v["mode"], 16)        # the oracle's reduction order: 16 / n lanes per knot row, 0 = batch kernel
         d = synth.make_systems(n, N, batch=2, seed=300 + n + N, nan_pads=True)
         cap, tol = (40, 1e-7) if N > 128 else (60, 1e-6)
         assert L.gbd_pcg_set_tuning(n, N, 0, C, v["mode"]) == 0
@@ -104,13 +105,13 @@ def test_every_fast_variant_bit_exact_vs_its_own_oracle(torch_cuda, capi, oracle
             for i in range(2):
                 l0 = d["lambda0"][i] if i == 0 else (0.1 * np.random.default_rng(i).standard_normal(n * N)).astype(np.float32)
                 got = _gpu_solve(torch_cuda, m, d["S"][i], d["Pinv"][i], d["gamma"][i], l0, n, N, cap, tol)
-                want = oracle_pcg.pcg_fast(d["S"][i], d["Pinv"][i], d["gamma"][i], l0, n, N, C, cap, tol)
+                want = oracle_pcg.pcg_fast(d["S"][i], d["Pinv"][i], d["gamma"][i], l0, n, N, C, cap, tol, lanes=lanes)
                 _assert_same(got, want, f"variant {v} system {i}")
                 assert np.isfinite(got["lam"]).all()
         finally:
             L.gbd_pcg_set_tuning(n, N, 0, 0, -1)
         seen += 1
-    assert seen >= 8
+    assert seen >= 25
 
 
 def test_golden_iiwa_systems_tolerance_parity_vs_reference_kernel(torch_cuda, capi, oracle_pcg):
@@ -175,19 +176,21 @@ def test_exit_semantics_and_warm_start(torch_cuda, capi, oracle_pcg):
     _assert_same(warm, oracle_pcg.pcg_fast(S, P, g, full["lam"], n, N, C, 173, 1e-7), "warm start")
 
 
-def test_batched_equals_single_and_is_deterministic(torch_cuda, capi, oracle_pcg):
+@pytest.mark.parametrize("C,mode", [(2, 20), (1, 26), (1, 27), (2, 28)])
+def test_batched_equals_single_and_is_deterministic(torch_cuda, capi, oracle_pcg, C, mode):
     """More systems than resident clusters, iteration counts from 1 to the cap (right-hand sides over six decades): clusters
     draw systems from the work counter in a data-dependent order, yet every system equals its own-oracle solution bit for
     bit, lands in its slot, and a second launch reproduces the first."""
     import mpcgpu_b200 as m
     torch = torch_cuda
-    n, N, B, cap, tol, C = 14, 32, 300, 60, 1e-4, 2
+    n, N, B, cap, tol = 14, 32, 300, 60, 1e-4
+    lanes = {26: n, 27: 0, 28: 0}.get(mode, 16)
     d = synth.make_systems(n, N, batch=B, seed=77, nan_pads=True)
     scale = (10.0 ** np.random.default_rng(5).uniform(-4.0, 2.0, size=B)).astype(np.float32)
     gam = (d["gamma"] * scale[:, None]).astype(np.float32)
     S, P, g = (_dev(torch, x) for x in (d["S"], d["Pinv"], gam))
     outs = []
-    assert capi.lib().gbd_pcg_set_tuning(n, N, 0, C, 20) == 0      # batches default to the v5 kernel; pin the fast one
+    assert capi.lib().gbd_pcg_set_tuning(n, N, 0, C, mode) == 0    # pin the kernel under test
     try:
         for _ in range(2):
             lam = _dev(torch, d["lambda0"])
@@ -201,7 +204,7 @@ def test_batched_equals_single_and_is_deterministic(torch_cuda, capi, oracle_pcg
     assert all(np.array_equal(a, b) for a, b in zip(outs[0], outs[1]))
     lam, it, fl = outs[0]
     for i in list(range(0, B, 7)) + [B - 1]:
-        want = oracle_pcg.pcg_fast(d["S"][i], d["Pinv"][i], gam[i], d["lambda0"][i], n, N, C, cap, tol)
+        want = oracle_pcg.pcg_fast(d["S"][i], d["Pinv"][i], gam[i], d["lambda0"][i], n, N, C, cap, tol, lanes=lanes)
         assert int(it[i]) == want["iters"] and bool(fl[i]) == want["max_iter_exit"], i
         assert np.array_equal(lam[i], want["lam"]), i
     assert it.min() <= 5 and fl.any()
@@ -238,3 +241,29 @@ def test_full_size_batch_properties(torch_cuda, capi, oracle_pcg):
         rf = oracle_pcg.rel_residual(d["S"][i], d["gamma"][i], lf[i], n, N)
         re_ = oracle_pcg.rel_residual(d["S"][i], d["gamma"][i], le[i], n, N)
         assert rf <= RESID_FACTOR * re_ + 1e-6
+
+
+@pytest.mark.parametrize("knots,block", [(32, 160), (64, 160), (128, 160), (32, 128), (64, 96), (128, 128)])
+def test_dropin_headers_fast_body_reference_launch_geometry(torch_cuda, oracle_pcg, tmp_path, knots, block):
+    """include/gbd_dropin built with -DGBD_DROPIN_FAST=1: pcg<float,14,N> launched exactly like include/pcg/sqp.cuh:230
+    (cooperative, grid = N, smem = pcgSharedMemSize).  Blocks of >= 160 threads run the tolerance-parity body (clusters of N/8
+    CTAs): bit-exact vs ITS oracle.  Smaller blocks run the bit-exact body: bit-exact vs the reference-order oracle."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_build", f"dropin_demo_fast_{knots}")
+    if not os.path.exists(exe):
+        pytest.skip("tests/_build/dropin_demo_fast_* not built (run __graft_entry__.build())")
+    n, cap, tol = 14, 167, 1e-5
+    d = synth.make_systems(n, knots, seed=9, nan_pads=True)
+    fin, fout = tmp_path / "in.bin", tmp_path / "out.bin"
+    np.concatenate([d["S"][0], d["Pinv"][0], d["gamma"][0], d["lambda0"][0]]).astype(np.float32).tofile(fin)
+    subprocess.check_call([exe, str(fin), str(fout), str(cap), repr(tol), str(block), "3"], timeout=120)
+    raw = np.fromfile(fout, np.float32)
+    vec = n * knots
+    tail = raw[3 * vec:].view(np.uint32)
+    got = dict(lam=raw[:vec], r=raw[vec:2 * vec], p=raw[2 * vec:3 * vec], iters=int(tail[0]), max_iter_exit=bool(tail[1]))
+    if block >= 160:
+        want = oracle_pcg.pcg_fast(d["S"][0], d["Pinv"][0], d["gamma"][0], d["lambda0"][0], n, knots, knots // 8, cap, tol)
+    else:
+        want = oracle_pcg.pcg(d["S"][0], d["Pinv"][0], d["gamma"][0], d["lambda0"][0], n, knots, cap, tol)
+    _assert_same(got, want, f"fast drop-in N={knots} block={block}")

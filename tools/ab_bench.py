@@ -99,7 +99,7 @@ def main():
                                 ours_window_us_median=float(np.median(w_ours[5:]))))
                 print(out[-1], flush=True)
     # batched kernels: every 2-CTA/SM build (modes 3 and 6) and the 1-CTA/SM builds at the same cluster size
-    for (n, N, B) in [(14, 128, 1024), (14, 32, 1024)]:
+    for (n, N, B) in [(14, 128, 1024), (14, 32, 1024)] + ([(14, 64, 1024), (14, 256, 512), (14, 512, 256)] if os.environ.get('AB_ALLBATCH') else []):
         cap, tol = CAPS[N], 1e-4
         d = synth.make_systems(n, N, batch=B, seed=1234)
         S, P, g = (torch.from_numpy(d[k]).cuda() for k in ("S", "Pinv", "gamma"))

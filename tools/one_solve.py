@@ -14,6 +14,9 @@ n, N = int(os.environ.get("STATE", "14")), int(os.environ.get("KNOTS", "128"))
 B = int(os.environ.get("BATCH", "256"))
 d = synth.make_systems(n, N, batch=max(B, 8), seed=3)
 S, P, g = (torch.from_numpy(d[k]).cuda() for k in ("S", "Pinv", "gamma"))
+if os.environ.get("TUNE_MODE"):                            # pin a kernel variant: TUNE_C (cluster size), TUNE_MODE (gbd_variants.h)
+    from mpcgpu_b200 import _capi
+    assert _capi.lib().gbd_pcg_set_tuning(n, N, 0, int(os.environ.get("TUNE_C", "0")), int(os.environ["TUNE_MODE"])) == 0
 it = torch.zeros(B, dtype=torch.int32, device="cuda")
 fl = torch.zeros(B, dtype=torch.uint8, device="cuda")
 for i in range(int(os.environ.get("SINGLES", "24"))):
