@@ -444,19 +444,28 @@ def run_ours(args):
                     "ours_over_reference_kernel_time": us_ref / (1e6 * kernel_s)}
                 # ---- the five exit tolerances of examples/track_iiwa_pcg.cu:62-68: ours (default numerics) and the reference kernel
                 sweep = []
+                nsw = min(nsys, 16)
+
+                def ours_sweep(q, tol):                             # the same systems the reference kernel gets, lambda0 = 0
+                    i = q % nsw
+                    lam[i].zero_()
+                    rc = L.gbd_pcg_solve_f32(n, N, dS[i].data_ptr(), dP[i].data_ptr(), dg[i].data_ptr(), lam[i].data_ptr(), 0, 0, 0, 0,
+                                             iters[i:].data_ptr(), flags[i:].data_ptr(), MAX_ITER, tol, stream)
+                    if rc:
+                        raise _capi.GbdPcgError(rc, "gbd_pcg_solve_f32")
+
                 for tol in SWEEP_TOLS:
-                    lam[:104].zero_()                               # every solve of the sweep starts from lambda0 = 0
-                    us_o = timed_us(lambda q: launch(q, tol), 96, warm=8)
-                    ito = iters[8:104].float().mean().item()
-                    capo = float((flags[8:104] != 0).float().mean().item())
+                    us_o = timed_us(lambda q: ours_sweep(q, tol), 48, warm=nsw) - t_zero
+                    ito = iters[:nsw].float().mean().item()
+                    capo = float((flags[:nsw] != 0).float().mean().item())
                     us_r = timed_us(lambda q: ref_launch(q, tol), 48, warm=4) - t_zero
                     itr = []
-                    for i in range(min(nsys, 16)):
+                    for i in range(nsw):
                         ref_launch(i, tol)
                         torch.cuda.synchronize()
                         itr.append(int(ref_ws.iters.item()))
-                    sweep.append({"pcg_exit_tol": tol, "ours_kernel_us": us_o, "ours_mean_iters": ito, "ours_max_iter_exit_frac": capo,
-                                  "reference_kernel_us": us_r, "reference_mean_iters": float(np.mean(itr))})
+                    sweep.append({"pcg_exit_tol": tol, "systems": nsw, "ours_kernel_us": us_o, "ours_mean_iters": ito,
+                                  "ours_max_iter_exit_frac": capo, "reference_kernel_us": us_r, "reference_mean_iters": float(np.mean(itr))})
                 extras["tolerance_sweep"] = sweep
             else:
                 extras["reference_gbdpcg"] = {"unavailable": "oracle/_ref/libref_gbdpcg.so not present (built only where /root/reference exists)"}
@@ -510,33 +519,38 @@ def run_ours(args):
             bsource = "synthetic LQR-like systems (mpcgpu_b200/synth.py)"
         bS, bP, bg = (torch.from_numpy(np.ascontiguousarray(hb[k])).to(dev) for k in ("S", "Pinv", "gamma"))
         Kb, Wb = args.batched_steps, 3
+        # rotating copies of the shard so that consecutive steps never find their inputs in L2 (a 128-system shard is 77 MB)
+        shard_bytes = Bl * 2 * 3 * n * n * N * esz
+        copies = 1 + max(1, -(-(256 << 20) // shard_bytes))
+        bSc = [bS] + [bS.clone() for _ in range(copies - 1)]
+        bPc = [bP] + [bP.clone() for _ in range(copies - 1)]
         blam = torch.zeros(Kb + Wb, Bl, n * N, device=dev)
         bit = torch.zeros(Kb + Wb, Bl, dtype=torch.int32, device=dev)
         bfl = torch.zeros(Kb + Wb, Bl, dtype=torch.uint8, device=dev)
         from mpcgpu_b200.sharding import ShardedBatch
         shard = ShardedBatch(n, N, BATCH_TOTAL, world, rank, dev)
         assert shard.local == Bl
-        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if Bl * 2 * 3 * n * n * N * esz < (160 << 20) else None
         rbat = _capi.resolved_variant(n, N, batched=True)
 
-        def bstep(s):
-            shard.iters, shard.flags = bit[s], bfl[s]
-            return shard.solve_step(bS, bP, bg, blam[s], MAX_ITER, EXIT_TOL)   # 1 launch + 1 all-gather of flags
-
-        for s in range(Wb):
-            bstep(s)
-        barrier()
-        tot_ms = 0.0
-        for s in range(Wb, Wb + Kb):
-            if flush is not None:
-                flush.fill_(s & 0xFF)                          # shard fits in L2: flush between timed iterations
+        def run_steps(first, count):
+            """`count` outer steps, pipelined as an SQP loop would: step s = one launch on the shard + the all-gather of its flags,
+            which overlaps step s+1's solve (it is waited for one step later).  Device time of the whole sequence, max over ranks."""
             b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             barrier()
             b0.record()
-            bstep(s)
+            pending = None
+            for s in range(first, first + count):
+                nxt = shard.solve_step_async(bSc[s % copies], bPc[s % copies], bg, blam[s], MAX_ITER, EXIT_TOL, iters=bit[s], flags=bfl[s])
+                if pending is not None:
+                    pending.wait()                              # the flags of step s-1: what the loop needs before it can plan step s+1
+                pending = nxt
+            gflags = pending.wait()
             b1.record()
             torch.cuda.synchronize()
-            tot_ms += max_over_ranks(b0.elapsed_time(b1))
+            return max_over_ranks(b0.elapsed_time(b1)), gflags
+
+        run_steps(0, Wb)
+        tot_ms, _ = run_steps(Wb, Kb)
         bi = sum_over_ranks(float(bit[Wb:].sum().item()))
         conv = sum_over_ranks(float((bfl[Wb:] == 0).sum().item())) / (world * Bl * Kb)
         bsec = tot_ms * 1e-3 / Kb
@@ -546,8 +560,9 @@ def run_ours(args):
                    "pcg_iters_per_sec": bi / Kb / bsec, "ms_per_step": 1e3 * bsec, "steps": Kb,
                    "mean_iters": bi / Kb / (world * Bl), "converged_frac": conv,
                    "kernel": f"{rbat['kernel']} (cluster {rbat['cluster']}, mode {rbat['mode']}, numerics {'fast' if rbat['fast'] else 'bitexact'})",
-                   "collective": "nccl all_gather of converged flags per step" if world > 1 else "none (1 rank)",
-                   "l2": "flushed between timed steps" if flush is not None else "inputs larger than L2",
+                   "collective": ("nccl all_gather of converged flags per step, overlapped with the next step's solve" if world > 1
+                                  else "none (1 rank)"),
+                   "l2": f"{copies} rotating copies of the shard's matrices ({copies * shard_bytes >> 20} MiB) > L2: every step reads cold tiles",
                    "roofline": {"bound": "hbm", "unit": "GB/s", "peak": peak,
                                 "achieved": Bl * esz * (2 * (3 * N - 2) * n * n + 4 * N * n) / bsec / 1e9,
                                 "frac": Bl * esz * (2 * (3 * N - 2) * n * n + 4 * N * n) / bsec / 1e9 / peak,
@@ -556,6 +571,19 @@ def run_ours(args):
                                 "fp32_fma_tflops": 2 * (bi / Kb / world) * fma_per_iter / bsec / 1e12,
                                 "fp32_fma_frac_of_peak": 2 * (bi / Kb / world) * fma_per_iter / bsec / 1e12 / 74.4,
                                 "fp32_peak_note": "148 SMs x 128 FMA/clk x 1.965 GHz = 74.4 TFLOP/s nominal"}}
+        # ---- the same steps with the bit-exact batch kernel (identical results to the reference kernel, system by system)
+        prev_num = _capi.set_numerics(_capi.NUMERICS_BITEXACT)
+        try:
+            rbx = _capi.resolved_variant(n, N, batched=True)
+            blam.zero_()                                        # every solve starts from lambda0 = 0, as in the default-numerics steps
+            run_steps(0, 1)
+            kx = min(Kb, 3)
+            x_ms, _ = run_steps(Wb, kx)
+            batched["bitexact"] = {"kernel": f"{rbx['kernel']} (cluster {rbx['cluster']}, mode {rbx['mode']})",
+                                   "traj_per_sec": world * Bl / (x_ms * 1e-3 / kx), "ms_per_step": x_ms / kx, "steps": kx,
+                                   "mean_iters": sum_over_ranks(float(bit[Wb:Wb + kx].sum().item())) / kx / (world * Bl)}
+        finally:
+            _capi.set_numerics(prev_num)
         # ---- the same batch as whole SQP linear-system steps (row f3): KKT blocks in, dz out; assembly -> solve -> dz per
         # shard in one enqueue, then the flag all-gather
         try:
@@ -572,8 +600,6 @@ def run_ours(args):
             barrier()
             s_ms = 0.0
             for q in range(Ks):
-                if flush is not None:
-                    flush.fill_(q & 0xFF)
                 s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 barrier()
                 s0.record()

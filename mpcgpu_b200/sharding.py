@@ -45,6 +45,42 @@ def gather_converged(local_not_converged, batch: int, world: int, rank: int, gro
     return out[:batch]
 
 
+class PendingFlags:
+    """The all-gather of one step's flags, in flight.  `wait()` makes the CURRENT stream (not the host) wait for it and returns the
+    [batch] uint8 `max_iter_exit` vector of the whole batch; until then the collective overlaps whatever is enqueued after it --
+    normally the next step's solve, which does not depend on it."""
+
+    def __init__(self, work, out, batch):
+        self._work, self._out, self._batch = work, out, batch
+
+    def wait(self):
+        if self._work is not None:
+            self._work.wait()
+            self._work = None
+        return self._out[: self._batch]
+
+
+def gather_converged_async(local_not_converged, batch: int, world: int, rank: int, group=None) -> PendingFlags:
+    """gather_converged without the stream-level wait: the collective is enqueued behind the work already on the current stream
+    (it needs this step's flags) and runs on the communicator's own stream."""
+    import torch
+    import torch.distributed as dist
+
+    per = -(-batch // world)
+    lo, hi = shard_range(batch, world, rank)
+    if local_not_converged.numel() != hi - lo or local_not_converged.dtype != torch.uint8:
+        raise ValueError("expected this rank's uint8 flags")
+    send = local_not_converged
+    if hi - lo != per:
+        send = torch.zeros(per, dtype=torch.uint8, device=local_not_converged.device)
+        send[: hi - lo] = local_not_converged
+    if world == 1:
+        return PendingFlags(None, send, batch)              # no copy, no collective: the flags are already where they are needed
+    out = torch.empty(world * per, dtype=torch.uint8, device=send.device)
+    work = dist.all_gather_into_tensor(out, send.contiguous(), group=group, async_op=True)
+    return PendingFlags(work, out, batch)
+
+
 class ShardedBatch:
     """This rank's shard of a batch of systems, resident on its GPU, plus the per-step collective."""
 
@@ -65,6 +101,17 @@ class ShardedBatch:
             solver.solve_batched(self.n, self.N, self.local, d_S, d_Pinv, d_gamma, d_lambda, self.iters, self.flags,
                                  max_iter, exit_tol)
         return gather_converged(self.flags[: self.local], self.batch, self.world, self.rank)
+
+    def solve_step_async(self, d_S, d_Pinv, d_gamma, d_lambda, max_iter: int, exit_tol: float, iters=None, flags=None) -> PendingFlags:
+        """solve_step for a pipelined outer loop: the launch and the collective are enqueued and the call returns; the collective
+        overlaps whatever the caller enqueues next.  `iters` / `flags` (per-step result slots of `local` elements) default to the
+        shard's own, which the next step overwrites."""
+        from . import solver
+        it = self.iters if iters is None else iters
+        fl = self.flags if flags is None else flags
+        if self.local:
+            solver.solve_batched(self.n, self.N, self.local, d_S, d_Pinv, d_gamma, d_lambda, it, fl, max_iter, exit_tol)
+        return gather_converged_async(fl[: self.local], self.batch, self.world, self.rank)
 
 
 class ShardedStep:

@@ -43,6 +43,10 @@ def _worker(rank, world, port, batch, q):
         # flag of system i is (i % 3 == 0): every rank must end up with the same global vector
         local = torch.tensor([1 if i % 3 == 0 else 0 for i in range(lo, hi)], dtype=torch.uint8)
         got = sharding.gather_converged(local, batch, world, rank)
+        # the pipelined form: two steps in flight, waited for in order, same answer
+        p1 = sharding.gather_converged_async(local, batch, world, rank)
+        p2 = sharding.gather_converged_async(1 - local, batch, world, rank)
+        assert p1.wait().tolist() == got.tolist() and p2.wait().tolist() == [1 - v for v in got.tolist()]
         q.put((rank, got.tolist()))
     finally:
         dist.destroy_process_group()
