@@ -175,7 +175,9 @@ __device__ __forceinline__ void pcg_cluster_v4_run(const PcgArgs<float> &a, unsi
     auto gather = [&](uint32_t part_off, uint32_t halo_off, uint32_t ep, T &edge) -> T {
         uint64_t q[PER], hq = 0;
         bool ok;
+        SpinGuard guard;
         do {
+            guard.tick();
             ok = true;
 #pragma unroll
             for (uint32_t m = 0; m < PER; ++m) {
@@ -267,7 +269,8 @@ __device__ __forceinline__ void pcg_cluster_v4_run(const PcgArgs<float> &a, unsi
         send_edge(K::PK_HR, r, ep);
         if (halo) {
             uint64_t hq;
-            do { hq = ld_packet(my_halo_pk + 8u * K::PK_HR); } while (!packet_ok(hq, ep));
+            SpinGuard guard;
+            do { guard.tick(); hq = ld_packet(my_halo_pk + 8u * K::PK_HR); } while (!packet_ok(hq, ep));
             *halo_xr = packet_val(hq);
         }
         T rh = halo ? *halo_xr : T(0);                      // register copy of the neighbour's boundary r element

@@ -124,7 +124,9 @@ __device__ __forceinline__ void pcg_cluster_v5_run(const PcgArgs<float> &a, unsi
     auto gather = [&](uint32_t part_off, uint32_t halo_off, uint32_t ep, T &e0, T &e1) -> T {
         uint64_t q[PER], h0 = 0, h1 = 0;
         bool ok;
+        SpinGuard guard;
         do {
+            guard.tick();
             ok = true;
 #pragma unroll
             for (uint32_t m = 0; m < PER; ++m) {
@@ -236,7 +238,9 @@ __device__ __forceinline__ void pcg_cluster_v5_run(const PcgArgs<float> &a, unsi
         T rh0 = T(0), rh1 = T(0);                          // register copies of the neighbour's boundary r elements
         if (halo) {
             uint64_t h0, h1;
+            SpinGuard guard;
             do {
+                guard.tick();
                 h0 = ld_packet(my_halo_pk + 8u * (K::PK_HR + j0));
                 h1 = ld_packet(my_halo_pk + 8u * (K::PK_HR + j1));
             } while (!(packet_ok(h0, ep) && packet_ok(h1, ep)));

@@ -16,6 +16,17 @@ namespace gbd {
 // ----------------------------------------------------------------------------- addressing
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// Every poll loop is bounded: a packet that never arrives (a peer that died, a mis-sized launch) ends the kernel with a trap -- the
+// launch fails and the C ABI returns GBD_PCG_ERR_CUDA -- instead of hanging the GPU.  2^26 polls is seconds; an exchange takes
+// a few hundred cycles.
+struct SpinGuard {
+    uint32_t spins = 0;
+    __device__ __forceinline__ void tick()
+    {
+        if (++spins > (1u << 26)) __trap();
+    }
+};
+
 // ---- shared memory through explicit 32-bit addresses.  Measured (profiles/r02_timeline_fastb.log): with many live registers the
 // compiler does not keep shared-memory base addresses in registers, it re-derives them -- S2UR SR_CgaCtaId for every block of
 // accesses through a C++ pointer, S2R SR_SWINHI for every store into a peer's shared memory -- and these special-register reads
@@ -119,17 +130,22 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
+    const uint32_t addr = smem_u32(bar);
+    SpinGuard guard;                      // try_wait suspends the thread for a hardware-defined time per attempt
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, P1;\n"
+            "}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (ok) break;
+        guard.tick();
+    }
 }
 
 // ----------------------------------------------------------------------------- arithmetic

@@ -44,7 +44,8 @@ struct Pkt<float> {
     static __device__ __forceinline__ float get(const unsigned long long *slot, uint32_t epoch)
     {
         unsigned long long w;
-        do { w = ld_pkt(slot); } while ((uint32_t)(w >> 32) != epoch);
+        SpinGuard guard;
+        do { guard.tick(); w = ld_pkt(slot); } while ((uint32_t)(w >> 32) != epoch);
         return __uint_as_float((uint32_t)w);
     }
 };
@@ -60,8 +61,9 @@ struct Pkt<double> {
     static __device__ __forceinline__ double get(const unsigned long long *slot, uint32_t epoch)
     {
         unsigned long long lo, hi;
-        do { lo = ld_pkt(slot); } while ((uint32_t)(lo >> 32) != epoch);
-        do { hi = ld_pkt(slot + 1); } while ((uint32_t)(hi >> 32) != epoch);
+        SpinGuard guard;
+        do { guard.tick(); lo = ld_pkt(slot); } while ((uint32_t)(lo >> 32) != epoch);
+        do { guard.tick(); hi = ld_pkt(slot + 1); } while ((uint32_t)(hi >> 32) != epoch);
         return __longlong_as_double((long long)((hi << 32) | (lo & 0xffffffffull)));
     }
 };
@@ -204,7 +206,9 @@ __device__ __forceinline__ uint32_t pcg_grid_body(const T *__restrict__ gS_all, 
             }
             const unsigned long long *mine = part_slot(base, cta, 0);     // [N partials | n from left | n from right]
             bool ok;
+            SpinGuard guard;
             do {
+                guard.tick();
                 ok = true;
 #pragma unroll
                 for (uint32_t q = 0; q < QMAX; ++q) {
