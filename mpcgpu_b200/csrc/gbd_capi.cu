@@ -150,7 +150,7 @@ Variant *find_variant(uint32_t n, uint32_t N, bool f64, bool batched)
         for (auto &v : variants()) {
             if (v.n != n || v.N != N || v.f64 != f64 || v.unusable || mode_is_fast(v.mode) != want_fast) continue;
             if (v.mode == 10 || v.mode == 14 || v.mode == gbdlib::MODE_FAST_PROF || v.mode == gbdlib::MODE_FAST_B_PROF) continue;      // timeline builds are never a default
-            if (gbdlib::mode_is_packed(v.mode)) continue;                                       // batch kernels: only by preference
+            if (gbdlib::mode_is_packed(v.mode)) continue;                                           // batch kernels: only by preference                                       // batch kernels: only by preference
             if (mode_is_grid(v.mode)) { if (!grid) grid = &v; continue; }                          // whole-GPU kernels last
             return &v;
         }
