@@ -383,6 +383,7 @@ __device__ __forceinline__ void pcg_cluster_fastb_run(const PcgArgs<float> &a, u
             stamp(2, out[0]);
             __syncthreads();
             stamp(3, out[0]);
+            uint64_t k0 = 0, k1 = 0;                                 // halo lanes: their two w packets
             if (!isP) {
                 // ---- w = S u on the own rows; the w.u products parked; boundary rows sent to the neighbours
                 stamp(14, v2[0]);
@@ -391,6 +392,7 @@ __device__ __forceinline__ void pcg_cluster_fastb_run(const PcgArgs<float> &a, u
                 const float wsum = warp_sum(own_products(a_own_r + U_MINUS_R, out));
                 if (lane == 0) sts_f32(a_wu + 4u * (warp - NW), wsum);
                 stamp(4, wsum);
+                __syncwarp();                                        // named barriers are warp-aligned: reconverge after lane-dependent code
                 named_bar_arrive(1, NP + 32);
                 if (send_l || send_r) {
                     const uint64_t ga = (send_l ? gaddr_l : gaddr_r) + par * HALO_PAR_BYTES;
@@ -401,47 +403,28 @@ __device__ __forceinline__ void pcg_cluster_fastb_run(const PcgArgs<float> &a, u
                             asm volatile("st.relaxed.cluster.u64 [%0], %1;" ::"l"(ga + EOFF[k]), "l"(pk) : "memory");
                         }
                 }
-                uint64_t k0 = 0, k1 = 0;
                 if (hl) {                                            // first touch of the slots now: a slot is seen sooner once polled
                     k0 = ld_packet_local(my_halo + par * HALO_PAR_BYTES);
                     k1 = ld_packet_local(my_halo + par * HALO_PAR_BYTES + 8u * XS);
                 }
                 stamp(5, out[0]);
-                named_bar_sync(2, NT);                               // sleep until the exchange warp has published the scalars
-                stamp(9, out[0]);
-                alpha = lds_f32(a_sc);
-                beta = lds_f32(a_sc + 4u);
-                done = lds_f32(a_sc + 8u) != 0.f;
-                if (hl) {
-                    uint32_t spins2 = 0;
-                    while (!(packet_ok(k0, ep) && packet_ok(k1, ep))) {
-                        k0 = ld_packet_local(my_halo + par * HALO_PAR_BYTES);
-                        k1 = ld_packet_local(my_halo + par * HALO_PAR_BYTES + 8u * XS);
-                        if (++spins2 > (1u << 24)) __trap();          // a lost packet is an error (launch failure), not a hang
-                    }
-                    hw = packet_val(k0);
-                    hw2 = packet_val(k1);
-                }
-                stamp(10, hw);
             } else if (!xw) {
                 // ---- P-warps: r.u of their rows while the S product runs, then asleep until the scalars are published
                 const float rsum = warp_sum(own_products(a_own_r, out));
                 if (lane == 0) sts_f32(a_ru + 4u * warp, rsum);
+                __syncwarp();
                 named_bar_arrive(3, NP);
-                named_bar_sync(2, NT);
-                stamp(9, out[0]);
-                alpha = lds_f32(a_sc);
-                beta = lds_f32(a_sc + 4u);
-                done = lds_f32(a_sc + 8u) != 0.f;
             } else {
                 // ---- exchange warp: scalars that only need the previous gamma and denominator, then r.u (both while the S product runs)
                 float rgam = first ? 0.f : rcp_fast(gam), qq = __fmul_rn(den, rgam);            // qq = 1 / alpha
                 asm volatile("" : "+f"(rgam), "+f"(qq));
                 const float rsum = warp_sum(own_products(a_own_r, out));
                 if (lane == 0) sts_f32(a_ru, rsum);
+                __syncwarp();
                 named_bar_sync(3, NP);                               // the other P-warps have parked their r.u sums
                 const float cg = role_sum(a_ru);
                 stamp(4, cg);
+                __syncwarp();
                 named_bar_sync(1, NP + 32);                          // the S-warps have parked their w.u sums
                 stamp(5, cg);
                 const float cd = role_sum(a_wu);
@@ -483,8 +466,30 @@ __device__ __forceinline__ void pcg_cluster_fastb_run(const PcgArgs<float> &a, u
                     sts_f32(a_sc + 8u, done ? 1.f : 0.f);
                 }
                 stamp(8, alpha);
+                __syncwarp();
                 named_bar_arrive(2, NT);
                 stamp(9, alpha);
+            }
+            if (!xw) {
+                // every warp but the exchange warp sleeps here until the scalars are published (ONE barrier site for both roles:
+                // compute-sanitizer's synccheck treats syncs on one barrier from different instructions as divergence)
+                __syncwarp();
+                named_bar_sync(2, NT);
+                stamp(9, out[0]);
+                alpha = lds_f32(a_sc);
+                beta = lds_f32(a_sc + 4u);
+                done = lds_f32(a_sc + 8u) != 0.f;
+                if (hl) {
+                    uint32_t spins2 = 0;
+                    while (!(packet_ok(k0, ep) && packet_ok(k1, ep))) {
+                        k0 = ld_packet_local(my_halo + par * HALO_PAR_BYTES);
+                        k1 = ld_packet_local(my_halo + par * HALO_PAR_BYTES + 8u * XS);
+                        if (++spins2 > (1u << 24)) __trap();          // a lost packet is an error (launch failure), not a hang
+                    }
+                    hw = packet_val(k0);
+                    hw2 = packet_val(k1);
+                }
+                stamp(10, hw);
             }
             first = false;
         };
