@@ -102,11 +102,36 @@ static float dot_fast_b(uint32_t n, uint32_t N, uint32_t C, const float *a, cons
     return tree_sum(part, C);
 }
 
+/* the grid kernel's reduction (gbd_grid_pcg_fast.cuh; n a multiple of 32, C = number of CTAs, R = N/C knot rows each): one thread per
+ * element in (row, element) order; every warp of 32 consecutive threads adds its products in an XOR butterfly (a balanced tree in
+ * lane order); the R n / 32 warp sums of a CTA, and then the C CTA sums, are added in balanced trees in ascending order */
+static float dot_fast_grid(uint32_t n, uint32_t N, uint32_t C, const float *a, const float *b)
+{
+    const uint32_t R = N / C, NW = R * n / 32;
+    float *part = (float *)malloc(C * sizeof(float));
+    for (uint32_t cr = 0; cr < C; cr++) {
+        float wsum[64];
+        for (uint32_t w = 0; w < NW; w++) {
+            float lanev[32];
+            for (uint32_t l = 0; l < 32; l++) {
+                const size_t i = (size_t)cr * R * n + (size_t)w * 32 + l;
+                lanev[l] = a[i] * b[i];
+            }
+            wsum[w] = tree_sum(lanev, 32);
+        }
+        part[cr] = tree_sum(wsum, NW);
+    }
+    const float tot = tree_sum(part, C);
+    free(part);
+    return tot;
+}
+
 /* the kernels' reduction of per-element products a[i]*b[i] (i over N*n) for cluster size C and G lanes per knot row
- * (G = 0: the batch kernel's order, above) */
+ * (G = 0: the batch kernel's order, G = 1: the grid kernel's order, above) */
 static float dot_fast(uint32_t n, uint32_t N, uint32_t C, uint32_t G, const float *a, const float *b)
 {
     if (G == 0) return dot_fast_b(n, N, C, a, b);
+    if (G == 1) return dot_fast_grid(n, N, C, a, b);
     const uint32_t R = N / C, NOWN = R * G, LN = NOWN >= 384 ? 16 : 8, PPL = NOWN / (2 * LN);
     float part[16];
     float *prod = (float *)malloc(NOWN * sizeof(float));
@@ -144,8 +169,13 @@ ORACLE_API int pcg_fast_oracle_g_f32(uint32_t n, uint32_t N, uint32_t C, uint32_
                                      float *lambda, uint32_t max_iter, float exit_tol, uint32_t *iters_out,
                                      uint8_t *max_iter_exit_out, float *r_out, float *p_out, float *eta_out)
 {
-    if (!S || !Pinv || !gamma || !lambda || n < 2 || n > 16 || C < 1 || C > 16 || N % C || N / C < 2) return -1;
-    if (n % 2 || (N / C) % 2 || (G != 16 && G != n && G != 0) || (G && ((N / C) * G) % 16) || (!G && (N / C) % 8)) return -1;
+    if (!S || !Pinv || !gamma || !lambda || n < 2 || C < 1 || N % C || N / C < 2 || n % 2) return -1;
+    if (G == 1) {                                      /* grid kernel: whole warps per knot row, power-of-two CTA count */
+        if (n % 32 || n > 64 || (C & (C - 1)) || (N / C) * n / 32 > 64) return -1;
+    } else {
+        if (n > 16 || C > 16) return -1;
+        if ((N / C) % 2 || (G != 16 && G != n && G != 0) || (G && ((N / C) * G) % 16) || (!G && (N / C) % 8)) return -1;
+    }
     const size_t len = (size_t)n * N;
     float *buf = (float *)calloc(7 * len, sizeof(float));
     if (!buf) return -1;

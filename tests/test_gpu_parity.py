@@ -294,7 +294,7 @@ def test_ab_against_unmodified_reference_kernel(torch_cuda, capi):
     import mpcgpu_b200 as m
     torch = torch_cuda
     for (n, N, cap, tol) in ((2, 3, 50, 1e-10), (6, 12, 60, 1e-6), (14, 32, 173, 1e-6), (14, 128, 167, 1e-4),
-                             (14, 128, 167, 1e-6), (14, 512, 67, 1e-5)):
+                             (14, 128, 167, 1e-6), (14, 512, 67, 1e-5), (64, 256, 40, 1e-6)):     # last: BASELINE config 5
         d = synth.make_systems(n, N, seed=40 + N, nan_pads=True)
         S, P, g, l0 = (_dev(torch, d[k][0]) for k in ("S", "Pinv", "gamma", "lambda0"))
         ref = refgpu.solve(n, N, S, P, g, l0, cap, tol, block=128)
