@@ -160,25 +160,32 @@ pcg_grid_kernel_fast(const GridArgs<float> ga)
         unpack2(add2(add2(acc[0], acc[1]), acc[2]), lo, hi);
         return __fadd_rn(lo, hi);
     };
-    // band row of the shared-memory matrix (w = S u, and the prologue S lambda0): the same six chains with scalar FMAs
+    // one tile of a band row of the shared-memory matrix (w = S u, and the prologue S lambda0): the tile's two half chains with scalar
+    // FMAs (the halves of a packed FMA are independent IEEE operations: same bits as chain_pairs); xrow = the window row it multiplies
+    auto chain_tile = [&](const float *xrow, uint32_t blk, float &lo, float &hi) {
+        float l = 0.f, h = 0.f;
+        const float *mb = srow + (size_t)blk * n * n;
+#pragma unroll 8
+        for (uint32_t q = 0; q < H / 2; ++q) {
+            const float4 f = reinterpret_cast<const float4 *>(xrow)[q];
+            const float *m = mb + (size_t)(2 * q) * n;
+            const float m0 = m[0], m1 = m[n], m2 = m[(size_t)H * n], m3 = m[(size_t)(H + 1) * n];
+            l = q == 0 ? __fmul_rn(m0, f.x) : __fmaf_rn(m0, f.x, l);
+            h = q == 0 ? __fmul_rn(m2, f.y) : __fmaf_rn(m2, f.y, h);
+            l = __fmaf_rn(m1, f.z, l);
+            h = __fmaf_rn(m3, f.w, h);
+        }
+        lo = l;
+        hi = h;
+    };
+    auto combine = [&](const float (&lo)[3], const float (&hi)[3]) -> float {
+        return __fadd_rn(__fadd_rn(__fadd_rn(lo[0], lo[1]), lo[2]), __fadd_rn(__fadd_rn(hi[0], hi[1]), hi[2]));
+    };
     auto chain_smem = [&](const float *xw) -> float {
         float lo[3], hi[3];
 #pragma unroll
-        for (uint32_t blk = 0; blk < 3; ++blk) { lo[blk] = 0.f; hi[blk] = 0.f; }
-#pragma unroll 4
-        for (uint32_t q = 0; q < H / 2; ++q) {
-#pragma unroll
-            for (uint32_t blk = 0; blk < 3; ++blk) {
-                const float4 f = reinterpret_cast<const float4 *>(xw + blk * XS)[q];
-                const float *m = srow + (size_t)(blk * n + 2 * q) * n;
-                const float m0 = m[0], m1 = m[n], m2 = m[(size_t)H * n], m3 = m[(size_t)(H + 1) * n];
-                lo[blk] = q == 0 ? __fmul_rn(m0, f.x) : __fmaf_rn(m0, f.x, lo[blk]);
-                hi[blk] = q == 0 ? __fmul_rn(m2, f.y) : __fmaf_rn(m2, f.y, hi[blk]);
-                lo[blk] = __fmaf_rn(m1, f.z, lo[blk]);
-                hi[blk] = __fmaf_rn(m3, f.w, hi[blk]);
-            }
-        }
-        return __fadd_rn(__fadd_rn(__fadd_rn(lo[0], lo[1]), lo[2]), __fadd_rn(__fadd_rn(hi[0], hi[1]), hi[2]));
+        for (uint32_t blk = 0; blk < 3; ++blk) chain_tile(xw + blk * XS, blk, lo[blk], hi[blk]);
+        return combine(lo, hi);
     };
     auto warp_sum = [&](float v) -> float {
 #pragma unroll
@@ -215,14 +222,26 @@ pcg_grid_kernel_fast(const GridArgs<float> ga)
         u = chain_regs(xr + g * XS);
         xu[(g + 1) * XS + pj] = u;
         ++epoch;
-        const float uh = halo_exchange(my_uh, K::DOT_WORDS + K::HALO_WORDS, u, epoch);
-        if (hl) xu[hrow * XS + pj] = uh;
+        const uint32_t par = epoch & 1u;
+        // the boundary rows of u leave for the neighbours now; the tile that needs the neighbour's row is multiplied LAST, so that the
+        // L2 round trip hides behind the two tiles that only need this CTA's own rows (the three tile chains of a row are independent)
+        if (hl) Pkt<float>::put(nb + K::DOT_WORDS + K::HALO_WORDS + (size_t)(par * 2 + nb_side) * n + j, u, epoch);
         // scalars that only need the previous gamma and denominator: off the dependent chain
         float rgam = first ? 0.f : rcp_fast(gam), q = __fmul_rn(den, rgam);
         asm volatile("" : "+f"(rgam), "+f"(q));
         __syncthreads();
-        w = chain_smem(xu + g * XS);
-        const uint32_t par = epoch & 1u;
+        const bool rot = g == 0;                                 // row 0 waits for its LEFT tile: order 1, 2, 0; the other rows 0, 1, 2
+        const uint32_t t0 = rot ? 1u : 0u, t1 = rot ? 2u : 1u, t2 = rot ? 0u : 2u;
+        float la, ha, lb, hb, lc, hc;
+        chain_tile(xu + (g + t0) * XS, t0, la, ha);
+        chain_tile(xu + (g + t1) * XS, t1, lb, hb);
+        if (hl) xu[hrow * XS + pj] = Pkt<float>::get(my_uh + (size_t)(par * 2 + my_side) * n + j, epoch);
+        __syncthreads();
+        chain_tile(xu + (g + t2) * XS, t2, lc, hc);
+        {
+            const float lo[3] = {rot ? lc : la, rot ? la : lb, rot ? lb : lc}, hi[3] = {rot ? hc : ha, rot ? ha : hb, rot ? hb : hc};
+            w = combine(lo, hi);
+        }
         if (hl) Pkt<float>::put(nb + K::DOT_WORDS + (size_t)(par * 2 + nb_side) * n + j, w, epoch);     // w boundary rows ride along
         const float sr = warp_sum(__fmul_rn(r, u)), sw = warp_sum(__fmul_rn(w, u));
         if (lane == 0) sums[warp] = make_float2(sr, sw);
