@@ -64,13 +64,13 @@ struct BcrArgs {
     uint32_t *dbg;        // timeline build only: %clock stamps [stamp][CTA][warp] (gbd_pcg_set_debug_buffer, tools/timeline_bcr.py)
 };
 
-template <uint32_t n, uint32_t N, uint32_t C, uint32_t MINB, bool PROF = false>
-__global__ void __launch_bounds__(BcrShape<n, N, C>::NT, MINB)
-bcr_cluster_kernel(const BcrArgs a)
+// The body is a __device__ function so that both the C-ABI kernel and the drop-in pcg<T,n,N> template (-DGBD_DROPIN_DIRECT=1) can wrap
+// it.  Called by exactly NT = 128 threads of every CTA of a C-CTA cluster; solves systems first_sys, first_sys + sys_stride, ...
+template <uint32_t n, uint32_t N, uint32_t C, bool PROF = false>
+__device__ __forceinline__ void bcr_cluster_body(const BcrArgs &a, float *bsm, uint32_t first_sys, uint32_t sys_stride)
 {
     using K = BcrShape<n, N, C>;
     constexpr uint32_t R = K::R, nn = K::nn, WC = K::WC, ROWF = K::ROWF, WF = K::WF, NT = K::NT;
-    extern __shared__ __align__(16) float bsm[];
     float *rows = bsm;                                   // R row records
     const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
     float *scratch = bsm + (size_t)R * ROWF + warp * K::SCRATCH;
@@ -123,7 +123,7 @@ bcr_cluster_kernel(const BcrArgs a)
         }
     };
 
-    for (uint32_t sys = cluster_idx(); sys < a.batch; sys += cluster_count()) {
+    for (uint32_t sys = first_sys; sys < a.batch; sys += sys_stride) {
         if (a.only_if && a.only_if[sys] == 0) continue;   // cluster-uniform: every CTA reads the same byte
         const float *gS = a.S + ((size_t)sys * N + (size_t)cr * R) * 3 * nn;
         const float *gb = a.gamma + (size_t)sys * N * n + (size_t)cr * R * n;
@@ -407,6 +407,14 @@ bcr_cluster_kernel(const BcrArgs a)
         for (uint32_t i = t; i < R * n; i += NT) gl[i] = rows[(size_t)(i / n) * ROWF + K::OFF_X + i % n];
         cluster_sync();                                    // nobody reloads rows while a peer may still read x / W
     }
+}
+
+template <uint32_t n, uint32_t N, uint32_t C, uint32_t MINB, bool PROF = false>
+__global__ void __launch_bounds__(BcrShape<n, N, C>::NT, MINB)
+bcr_cluster_kernel(const BcrArgs a)
+{
+    extern __shared__ __align__(16) float bsm[];
+    bcr_cluster_body<n, N, C, PROF>(a, bsm, cluster_idx(), cluster_count());
 }
 
 }  // namespace gbd

@@ -17,6 +17,7 @@
 #include "gbd/gbd_cluster_pcg_v4.cuh"
 #include "gbd/gbd_cluster_pcg_v5.cuh"
 #include "gbd/gbd_cluster_pcg_fast.cuh"
+#include "gbd/gbd_bcr.cuh"
 
 // Numerics of the drop-in pcg<T,n,N>.  Default (0): bit-identical to the reference kernel.  -DGBD_DROPIN_FAST=1: the tolerance-parity
 // kernel of gbd_cluster_pcg_fast.cuh (same contract, iteration count within +-2, lambda within 1e-3 relative: include/gbd_pcg.h)
@@ -26,6 +27,15 @@
 // sets cudaFuncAttributeNonPortableClusterSizeAllowed on the kernel.
 #ifndef GBD_DROPIN_FAST
 #define GBD_DROPIN_FAST 0
+#endif
+
+// -DGBD_DROPIN_DIRECT=1: pcg<T,n,N> does not iterate at all -- the block-tridiagonal system is solved DIRECTLY by block cyclic reduction
+// in one thread-block cluster (include/gbd/gbd_bcr.cuh, the GPU counterpart of the reference's CPU QDLDL path; no preconditioner, no
+// cap), for fp32, n <= 15, power-of-two N = 32 / 64 / 128 and the reference's default block of exactly 128 threads.  *d_iters = 0 and
+// *d_max_iter_exit = false on return.  This is an experiment switch for the closed loop (profiles/r02_closed_loop.json): on the
+// reference's IIWA systems PCG often stops at its iteration cap, and this shows what exact solves do to tracking.
+#ifndef GBD_DROPIN_DIRECT
+#define GBD_DROPIN_DIRECT 0
 #endif
 
 #ifndef GBD_PCG_MAX_BLOCK
@@ -86,6 +96,21 @@ constexpr size_t fastcg_smem(size_t n, size_t N, size_t e)
     const size_t C = fastcg_cluster(n, N, e), R = C ? N / C : 0;
     return C ? 32 + 2 * C * 16 + R * 16 * 8 + 2 * (2 * 2 * 16) * 8 + 4 * ((R + 6) + (R + 4) + (R + 2)) * 16 + 4 * ((R + 4) + (R + 2)) * 3 * n * n : 0;
 }
+// direct body (GBD_DROPIN_DIRECT): CTAs per system, 0 = not available
+constexpr size_t direct_cluster(size_t n, size_t N, size_t e)
+{
+#ifdef GBD_DROPIN_NO_CLUSTER
+    return 0;
+#else
+    return (GBD_DROPIN_DIRECT && e == 4 && n + 1 <= 16 && (N == 32 || N == 64 || N == 128)) ? N / 8 : 0;
+#endif
+}
+constexpr size_t direct_smem(size_t n, size_t N, size_t e)
+{
+    const size_t C = direct_cluster(n, N, e), R = C ? N / C : 0, p4 = 3;
+    const size_t wf = (n * (2 * n + 1) + p4) / 4 * 4, rowf = (3 * n * n + n + p4) / 4 * 4 + wf + (n + p4) / 4 * 4;
+    return C ? 4 * (R * rowf + 4 * (2 * wf + 32)) : 0;
+}
 constexpr bool fast_shape(size_t n, size_t N, size_t e)
 {
 #ifdef GBD_DROPIN_NO_CLUSTER
@@ -110,11 +135,15 @@ constexpr size_t grid_rows(size_t n, size_t N, size_t e)     // knot rows per CT
 //         RG = 8 when the block has >= 8 row groups of threads, else 1.  CTAs beyond N/RG return.
 template <typename T, uint32_t n, uint32_t N>
 struct Shape {
-    static constexpr uint32_t CCG = (uint32_t)fastcg_cluster(n, N, sizeof(T));
+    static constexpr uint32_t CDIR = (uint32_t)direct_cluster(n, N, sizeof(T));
+    static constexpr bool DIRECT = CDIR != 0;
+    using Direct = gbd::BcrShape<DIRECT ? n : 2, DIRECT ? N : 4, DIRECT ? CDIR : 1>;
+    static_assert(!DIRECT || Direct::SMEM_BYTES == direct_smem(n, N, sizeof(T)), "run-time smem formula out of sync");
+    static constexpr uint32_t CCG = DIRECT ? 0u : (uint32_t)fastcg_cluster(n, N, sizeof(T));
     static constexpr bool FASTCG = CCG != 0;
-    static constexpr bool FAST = !FASTCG && fast_shape(n, N, sizeof(T));
-    static constexpr bool FAST4 = !FASTCG && fast4_shape(n, N, sizeof(T));
-    static constexpr uint32_t C = FASTCG ? CCG : (FAST4 ? N / 8 : (FAST ? N / 16 : 1));
+    static constexpr bool FAST = !FASTCG && !DIRECT && fast_shape(n, N, sizeof(T));
+    static constexpr bool FAST4 = !FASTCG && !DIRECT && fast4_shape(n, N, sizeof(T));
+    static constexpr uint32_t C = DIRECT ? CDIR : (FASTCG ? CCG : (FAST4 ? N / 8 : (FAST ? N / 16 : 1)));
     using FastCg = gbd::ClusterPcgFast<FASTCG ? n : 2, FASTCG ? N : 8, FASTCG ? CCG : 2>;
     static constexpr uint32_t NT_FASTCG = FASTCG ? FastCg::NT : 0;
     static_assert(!FASTCG || (FastCg::SMEM_BYTES == fastcg_smem(n, N, sizeof(T)) && FastCg::NT == fastcg_threads(n, N, sizeof(T))), "run-time smem formula out of sync");
@@ -138,7 +167,8 @@ struct Shape {
     static constexpr size_t SMEM_G1 = gbd::GridPcg<T, n, N, 1>::SMEM_BYTES;
     static constexpr size_t SMEM_GR = gbd::GridPcg<T, n, N, RG>::SMEM_BYTES;
     static constexpr size_t SMEM_BASE = SMEM_FAST > (SMEM_G1 > SMEM_GR ? SMEM_G1 : SMEM_GR) ? SMEM_FAST : (SMEM_G1 > SMEM_GR ? SMEM_G1 : SMEM_GR);
-    static constexpr size_t SMEM_BYTES = (FASTCG && FastCg::SMEM_BYTES > SMEM_BASE) ? FastCg::SMEM_BYTES : SMEM_BASE;
+    static constexpr size_t SMEM_CG = (FASTCG && FastCg::SMEM_BYTES > SMEM_BASE) ? FastCg::SMEM_BYTES : SMEM_BASE;
+    static constexpr size_t SMEM_BYTES = (DIRECT && Direct::SMEM_BYTES > SMEM_CG) ? Direct::SMEM_BYTES : SMEM_CG;
 };
 // packet workspace + epoch counter of one instantiation (zero-initialised by the loader); R = 1 is the largest layout
 template <typename T, uint32_t n, uint32_t N>
@@ -157,6 +187,18 @@ pcg(T *d_S, T *d_Pinv, T *d_gamma, T *d_lambda, T *d_r, T *d_p, T *d_v_temp, T *
     extern __shared__ __align__(16) unsigned char gbd_dropin_smem[];
     (void)d_v_temp; (void)d_eta_new_temp;          // reference scratch for its smem trees; not needed here
     uint8_t *d_flag = reinterpret_cast<uint8_t *>(d_max_iter_exit);
+    if constexpr (SH::DIRECT) {
+        if (blockDim.x == SH::Direct::NT) {
+            if (gbd::cluster_idx() != 0) return;                  // whole clusters leave together
+            const gbd::BcrArgs ba{d_S, d_gamma, d_lambda, 1u, nullptr, nullptr};
+            gbd::bcr_cluster_body<state_size, knot_points, SH::CDIR>(ba, reinterpret_cast<float *>(gbd_dropin_smem), 0u, 1u);
+            if (gbd::cluster_ctarank() == 0 && threadIdx.x == 0) {
+                *d_iters = 0u;
+                *d_flag = 0;
+            }
+            return;
+        }
+    }
     if constexpr (SH::FASTCG) {
         if (blockDim.x >= SH::NT_FASTCG) {
             if (gbd::cluster_idx() != 0) return;                  // whole clusters leave together
@@ -233,6 +275,7 @@ size_t pcgSharedMemSize(uint32_t state_size, uint32_t knot_points)
     const size_t rg = gbd_dropin::grid_rows(n, N, e);
     if (rg > 1 && gbd_dropin::grid_smem(n, N, rg, e) > need) need = gbd_dropin::grid_smem(n, N, rg, e);
     if (gbd_dropin::fastcg_smem(n, N, e) > need) need = gbd_dropin::fastcg_smem(n, N, e);
+    if (gbd_dropin::direct_smem(n, N, e) > need) need = gbd_dropin::direct_smem(n, N, e);
     return need;
 }
 

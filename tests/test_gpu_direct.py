@@ -123,3 +123,32 @@ def test_step_with_direct_fallback(torch_cuda, oracle_pcg):
             assert np.array_equal(out[True][1][i], schur.dz(o["Ginv"], kk[i][1], kk[i][2], out[True][0][i], n, m, N))
         else:
             assert np.array_equal(out[True][0][i], out[False][0][i]) and np.array_equal(out[True][1][i], out[False][1][i])
+
+
+@pytest.mark.parametrize("knots,block", [(32, 128), (128, 128), (128, 64)])
+def test_dropin_headers_direct_body_reference_launch_geometry(torch_cuda, oracle_pcg, tmp_path, knots, block):
+    """include/gbd_dropin built with -DGBD_DROPIN_DIRECT=1: pcg<float,14,N> launched exactly like include/pcg/sqp.cuh:230 solves the
+    system by block cyclic reduction (block of 128 threads: bit-identical to the C-ABI direct solver, iters = 0, flag = 0); any
+    other block size runs the bit-exact PCG body."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_build", f"dropin_demo_direct_{knots}")
+    if not os.path.exists(exe):
+        pytest.skip("tests/_build/dropin_demo_direct_* not built (run __graft_entry__.build())")
+    n, cap, tol = 14, 167, 1e-5
+    d = synth.make_systems(n, knots, seed=9, nan_pads=True)
+    fin, fout = tmp_path / "in.bin", tmp_path / "out.bin"
+    np.concatenate([d["S"][0], d["Pinv"][0], d["gamma"][0], d["lambda0"][0]]).astype(np.float32).tofile(fin)
+    subprocess.check_call([exe, str(fin), str(fout), str(cap), repr(tol), str(block), "3"], timeout=120)
+    raw = np.fromfile(fout, np.float32)
+    vec = n * knots
+    tail = raw[3 * vec:].view(np.uint32)
+    lam, iters, flag = raw[:vec], int(tail[0]), bool(tail[1])
+    if block == 128:
+        assert iters == 0 and not flag
+        assert np.array_equal(lam, _solve(torch_cuda, n, knots, d["S"][0], d["gamma"][0]))
+        truth = oracle_pcg.solve_f64(d["S"][0], d["gamma"][0], n, knots)
+        assert np.abs(lam - truth).max() / np.abs(truth).max() < 1e-3
+    else:
+        want = oracle_pcg.pcg(d["S"][0], d["Pinv"][0], d["gamma"][0], d["lambda0"][0], n, knots, cap, tol)
+        assert iters == want["iters"] and flag == want["max_iter_exit"] and np.array_equal(lam, want["lam"])

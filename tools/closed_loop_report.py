@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Summarise the closed-loop MPC runs written by tools/gpu_closed_loop.sh (gpurun_out/cl_<arm>_<mode>_<knots>.bin) into
 profiles/r02_closed_loop.json.  Arms: ref = reference GBD-PCG headers, dropin = include/gbd_dropin (bit-exact bodies), fast =
-include/gbd_dropin with -DGBD_DROPIN_FAST=1, refp = reference headers with pcg_exit_tol x 1.001 (the experiment's noise floor).
+include/gbd_dropin with -DGBD_DROPIN_FAST=1, direct = include/gbd_dropin with -DGBD_DROPIN_DIRECT=1 (block cyclic reduction instead of PCG), refp = reference headers with pcg_exit_tol x 1.001 (the experiment's noise floor).
 Modes: b = behaviour build (TIME_LINSYS=0: SQP iterations per control step), t = timing build (the reference's linsys stopwatch)."""
 import json
 import os
@@ -37,7 +37,7 @@ for knots, tol in ((32, 5e-6), (128, 1e-4)):
         ref = load("ref", mode, knots)
         if ref is None:
             continue
-        for arm in ("ref", "dropin", "fast", "refp"):
+        for arm in ("ref", "dropin", "fast", "direct", "refp"):
             d = load(arm, mode, knots)
             if d is None:
                 continue

@@ -6,7 +6,7 @@
 mkdir -p gpurun_out
 cd oracle/_ref/run
 KNOTS_LIST=${KNOTS_LIST:-"32 128"}
-ARMS=${ARMS:-"ref dropin fast refp"}
+ARMS=${ARMS:-"ref dropin fast direct refp"}
 MODES=${MODES:-"b t"}
 for K in $KNOTS_LIST; do
   if [ "$K" = "32" ]; then TOL=5e-6; ROWS=${ROWS32:-140}; else TOL=1e-4; ROWS=${ROWS128:-200}; fi
