@@ -22,13 +22,19 @@
 
 namespace gbd {
 
-template <uint32_t n, uint32_t N, uint32_t R>
+// CL = CTAs per thread-block cluster (1: no clusters).  With CL > 1 the all-gather is two-level: pairs meet in the cluster leader's shared
+// memory (DSMEM), the CTAS / CL leaders exchange cluster sums through L2, every leader hands the total to its peers (DSMEM) -- fewer
+// participants on the L2 path (its cost follows their number: profiles/r01c_micro_l2_exchange.log), same balanced tree (CL a power of two).
+template <uint32_t n, uint32_t N, uint32_t R, uint32_t CL = 1>
 struct GridPcgFast {
     using T = float;
     static_assert(n % 32 == 0 && n <= 64, "a knot row is n/32 whole warps; its Pinv row (3n floats) lives in registers");
     static_assert(N % R == 0 && R >= 2, "two boundary rows per CTA");
     static constexpr uint32_t CTAS = N / R;
     static_assert(CTAS >= 2 && (CTAS & (CTAS - 1)) == 0, "the pair tree assumes a power-of-two CTA count");
+    static_assert(CL >= 1 && (CL & (CL - 1)) == 0 && CTAS % CL == 0 && CL <= 8, "cluster size");
+    static constexpr uint32_t NCL = CTAS / CL;           // clusters = participants of the L2 exchange
+    static_assert(NCL <= 32 || CL == 1, "one cluster sum per lane of the leader's first warp");
     static constexpr uint32_t NT = R * n, NW = NT / 32, H = n / 2, XS = n, TILE = 3 * n * n;
     static_assert((NW & (NW - 1)) == 0 && NW <= 32, "warp sums are added in a balanced tree");
     static constexpr bool TMA_OK = (TILE * sizeof(T)) % 16 == 0;
@@ -39,7 +45,8 @@ struct GridPcgFast {
     static constexpr size_t a16(size_t x) { return (x + 15) / 16 * 16; }
     static constexpr size_t OFF_BAR = 0;
     static constexpr size_t OFF_SUM = 16;                                   // [NW] {r.u, w.u} warp sums
-    static constexpr size_t OFF_PAIRS = OFF_SUM + a16(8 * NW);              // [CTAS] {gamma_c, delta_c}
+    static constexpr size_t OFF_INBOX = OFF_SUM + a16(8 * NW);              // [2][CL] x 16 B pairs from the cluster's CTAs (leader), then [2] x 16 B total
+    static constexpr size_t OFF_PAIRS = OFF_INBOX + 16 * (2 * CL + 2);      // [CTAS] {gamma_c, delta_c}   (CL > 1: [0] = the total)
     static constexpr size_t OFF_XR = OFF_PAIRS + a16(8 * CTAS);             // r rows a-1 .. a+R, interleaved pairs
     static constexpr size_t OFF_XU = OFF_XR + a16(4 * (R + 2) * XS);        // u rows a-1 .. a+R (prologue: lambda0)
     static constexpr size_t OFF_S = OFF_XU + a16(4 * (R + 2) * XS);         // S rows a .. a+R-1
@@ -59,12 +66,12 @@ __device__ __forceinline__ void ld_pkt2(const unsigned long long *p, unsigned lo
     asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
 
-template <uint32_t n, uint32_t N, uint32_t R>
-__global__ void __launch_bounds__(GridPcgFast<n, N, R>::NT, 1)
+template <uint32_t n, uint32_t N, uint32_t R, uint32_t CL = 1>
+__global__ void __launch_bounds__(GridPcgFast<n, N, R, CL>::NT, 1)
 pcg_grid_kernel_fast(const GridArgs<float> ga)
 {
-    using K = GridPcgFast<n, N, R>;
-    constexpr uint32_t CTAS = K::CTAS, NT = K::NT, NW = K::NW, H = K::H, XS = K::XS, TILE = K::TILE;
+    using K = GridPcgFast<n, N, R, CL>;
+    constexpr uint32_t CTAS = K::CTAS, NT = K::NT, NW = K::NW, H = K::H, XS = K::XS, TILE = K::TILE, NCL = K::NCL;
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const PcgArgs<float> &a = ga.a;
@@ -101,7 +108,9 @@ pcg_grid_kernel_fast(const GridArgs<float> ga)
             mbar_init(barT, 1);
             fence_mbar_init();
         }
+        if (t < 4 * (2 * CL + 2)) reinterpret_cast<uint32_t *>(smem_raw + K::OFF_INBOX)[t] = 0u;      // epoch 0 is never sent
         __syncthreads();
+        if constexpr (CL > 1) cluster_sync();               // inboxes cleared before any peer writes into them
         const bool tma = K::TMA_OK && a.use_tma;
         if (tma) {
             if (t == 0) {
@@ -246,35 +255,91 @@ pcg_grid_kernel_fast(const GridArgs<float> ga)
         const float sr = warp_sum(__fmul_rn(r, u)), sw = warp_sum(__fmul_rn(w, u));
         if (lane == 0) sums[warp] = make_float2(sr, sw);
         __syncthreads();
-        {   // the CTA's pair (balanced tree over its warp sums), one 16-byte packet to every consumer CTA; then poll this CTA's own
+        float gam_new, del_new;
+        {   // the CTA's pair: balanced tree over its warp sums (every thread, same bits)
             float vg[NW], vd[NW];
 #pragma unroll
             for (uint32_t i = 0; i < NW; ++i) { const float2 f = sums[i]; vg[i] = f.x; vd[i] = f.y; }
             const float cg = tree_sum<NW>(vg), cd = tree_sum<NW>(vd);
-            for (uint32_t c = t; c < CTAS; c += NT) st_pkt2(ga.ws + K::REGION_WORDS * c + (size_t)(par * CTAS + cta) * 2, cg, cd, epoch);
-            for (uint32_t c = t; c < CTAS; c += NT) {
-                unsigned long long pa, pb;
-                SpinGuard guard;
+            if constexpr (CL == 1) {
+                // one 16-byte packet to every consumer CTA; then poll this CTA's own region
+                for (uint32_t c = t; c < CTAS; c += NT) st_pkt2(ga.ws + K::REGION_WORDS * c + (size_t)(par * CTAS + cta) * 2, cg, cd, epoch);
+                for (uint32_t c = t; c < CTAS; c += NT) {
+                    unsigned long long pa, pb;
+                    SpinGuard guard;
+                    do {
+                        guard.tick();
+                        ld_pkt2(my + (size_t)(par * CTAS + c) * 2, pa, pb);
+                    } while ((uint32_t)(pa >> 32) != epoch || (uint32_t)(pb >> 32) != epoch);
+                    pairs[c] = make_float2(__uint_as_float((uint32_t)pa), __uint_as_float((uint32_t)pb));
+                }
+            } else if (warp == 0) {
+                // two-level: (1) the pair to the cluster leader's inbox (DSMEM); the leader adds its cluster's CL pairs in rank order,
+                // (2) exchanges cluster sums with the other leaders through L2 and adds them (one per lane + butterfly = the balanced
+                // tree), (3) hands the total to every CTA of its cluster (DSMEM); (4) every CTA polls its own total slot
+                const uint32_t inbox_u = smem_u32(smem_raw + K::OFF_INBOX), crank = cluster_ctarank(), cl_id = cta / CL;
+                if (lane == 0) st_pair_cluster(map_to_cta(inbox_u, 0) + 16u * (par * CL + crank), cg, cd, epoch);
+                if (crank == 0) {
+                    float lg[CL], ld[CL];
+                    bool ok;
+                    SpinGuard guard;
+                    do {
+                        guard.tick();
+                        ok = true;
+#pragma unroll
+                        for (uint32_t m = 0; m < CL; ++m) {
+                            const uint4 q4 = ld_pair(inbox_u + 16u * (par * CL + m));
+                            ok = ok && q4.y == epoch && q4.w == epoch;
+                            lg[m] = __uint_as_float(q4.x);
+                            ld[m] = __uint_as_float(q4.z);
+                        }
+                    } while (!ok);
+                    const float clg = tree_sum<CL>(lg), cld = tree_sum<CL>(ld);
+                    if (lane < NCL) st_pkt2(ga.ws + K::REGION_WORDS * (lane * CL) + (size_t)(par * CTAS + cl_id) * 2, clg, cld, epoch);
+                    float tg = 0.f, td = 0.f;
+                    if (lane < NCL) {
+                        unsigned long long pa, pb;
+                        SpinGuard g2;
+                        do {
+                            g2.tick();
+                            ld_pkt2(my + (size_t)(par * CTAS + lane) * 2, pa, pb);
+                        } while ((uint32_t)(pa >> 32) != epoch || (uint32_t)(pb >> 32) != epoch);
+                        tg = __uint_as_float((uint32_t)pa);
+                        td = __uint_as_float((uint32_t)pb);
+                    }
+                    tg = warp_sum(tg);
+                    td = warp_sum(td);
+                    if (lane < CL) st_pair_cluster(map_to_cta(inbox_u, lane) + 16u * (2 * CL + par), tg, td, epoch);
+                }
+                uint4 q4;
+                SpinGuard g3;
                 do {
-                    guard.tick();
-                    ld_pkt2(my + (size_t)(par * CTAS + c) * 2, pa, pb);
-                } while ((uint32_t)(pa >> 32) != epoch || (uint32_t)(pb >> 32) != epoch);
-                pairs[c] = make_float2(__uint_as_float((uint32_t)pa), __uint_as_float((uint32_t)pb));
+                    g3.tick();
+                    q4 = ld_pair(inbox_u + 16u * (2 * CL + par));
+                } while (q4.y != epoch || q4.w != epoch);
+                if (lane == 0) pairs[0] = make_float2(__uint_as_float(q4.x), __uint_as_float(q4.z));
             }
         }
         if (hl) w2 = Pkt<float>::get(my_wh + (size_t)(par * 2 + my_side) * n + j, epoch);
         __syncthreads();
-        // every warp adds the CTAS pairs in the same balanced tree (ascending CTA order): PL consecutive pairs per lane, then a butterfly
-        constexpr uint32_t PL = CTAS >= 32 ? CTAS / 32 : 1;
-        float vg[PL], vd[PL];
+        if constexpr (CL == 1) {
+            // every warp adds the CTAS pairs in the same balanced tree (ascending CTA order): PL consecutive pairs per lane, then a butterfly
+            constexpr uint32_t PL = CTAS >= 32 ? CTAS / 32 : 1;
+            float vg[PL], vd[PL];
 #pragma unroll
-        for (uint32_t i = 0; i < PL; ++i) {
-            const uint32_t c = lane * PL + i;
-            const float2 f = c < CTAS ? pairs[c] : make_float2(0.f, 0.f);
-            vg[i] = f.x;
-            vd[i] = f.y;
+            for (uint32_t i = 0; i < PL; ++i) {
+                const uint32_t c = lane * PL + i;
+                const float2 f = c < CTAS ? pairs[c] : make_float2(0.f, 0.f);
+                vg[i] = f.x;
+                vd[i] = f.y;
+            }
+            gam_new = warp_sum(tree_sum<PL>(vg));
+            del_new = warp_sum(tree_sum<PL>(vd));
+        } else {
+            const float2 f = pairs[0];
+            gam_new = f.x;
+            del_new = f.y;
         }
-        const float gam_new = warp_sum(tree_sum<PL>(vg)), del_new = warp_sum(tree_sum<PL>(vd));
         done = !first && fabsf(gam_new) < a.exit_tol;                                        // pcg.cuh:195
         if (first) {
             beta = 0.f;
@@ -305,6 +370,7 @@ pcg_grid_kernel_fast(const GridArgs<float> ga)
     if (a.r_out) a.r_out[o] = r;
     if (a.p_out) a.p_out[o] = p;
     if (cta == 0 && t == 0) store_result(a, 0, iter, max_iter_exit);
+    if constexpr (CL > 1) cluster_sync();                   // no CTA leaves while a peer may still write into its shared memory
 }
 
 }  // namespace gbd

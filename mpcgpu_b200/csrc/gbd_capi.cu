@@ -150,7 +150,8 @@ Variant *find_variant(uint32_t n, uint32_t N, bool f64, bool batched)
         for (auto &v : variants()) {
             if (v.n != n || v.N != N || v.f64 != f64 || v.unusable || mode_is_fast(v.mode) != want_fast) continue;
             if (v.mode == 10 || v.mode == 14 || v.mode == gbdlib::MODE_FAST_PROF || v.mode == gbdlib::MODE_FAST_B_PROF) continue;      // timeline builds are never a default
-            if (gbdlib::mode_is_packed(v.mode)) continue;                                           // batch kernels: only by preference                                       // batch kernels: only by preference
+            if (gbdlib::mode_is_packed(v.mode)) continue;                                           // batch kernels: only by preference
+            if (v.mode == gbdlib::MODE_FAST_GRID2) continue;                                        // measured slower than the flat exchange: only by tuning                                       // batch kernels: only by preference
             if (mode_is_grid(v.mode)) { if (!grid) grid = &v; continue; }                          // whole-GPU kernels last
             return &v;
         }
@@ -191,6 +192,19 @@ int prepare(Variant &v)
         static const int cap = [] { const char *e = getenv("GBD_PCG_MAX_CLUSTER"); return e ? atoi(e) : 0; }();
         max_clusters(v, &v.resident);
         v.unusable = v.resident < 1 || (cap > 0 && (int)v.C > cap);
+    } else if (v.grid_cluster > 1) {
+        // a clustered grid kernel needs ALL its clusters co-resident (they poll each other): usable only if the device can hold them
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute at[1];
+        cfg.gridDim = dim3(v.C);
+        cfg.blockDim = dim3(v.nt);
+        cfg.dynamicSmemBytes = v.smem;
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = v.grid_cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int nc = 0;
+        if (cudaOccupancyMaxActiveClusters(&nc, v.kernel, &cfg) != cudaSuccess) { cudaGetLastError(); nc = 0; }
+        v.unusable = (uint32_t)nc * v.grid_cluster < v.C;
     }
     v.prepared = true;
     return GBD_PCG_OK;
@@ -246,7 +260,7 @@ int launch_grid(Variant &v, uint32_t batch, const T *S, const T *P, const T *g, 
             w->epoch += 2u * max_iter + 4u;                  // upper bound on the phases one launch can use
         }
         cudaLaunchConfig_t cfg = {};
-        cudaLaunchAttribute at[1];
+        cudaLaunchAttribute at[2];
         cfg.gridDim = dim3(v.C);
         cfg.blockDim = dim3(v.nt);
         cfg.dynamicSmemBytes = v.smem;
@@ -254,6 +268,11 @@ int launch_grid(Variant &v, uint32_t batch, const T *S, const T *P, const T *g, 
         at[0].id = cudaLaunchAttributeCooperative;           // co-residency of all CTAs (they poll each other)
         at[0].val.cooperative = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
+        if (v.grid_cluster > 1) {                            // two-level exchange: DSMEM inside clusters, L2 between their leaders
+            at[1].id = cudaLaunchAttributeClusterDimension;
+            at[1].val.clusterDim.x = v.grid_cluster; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
+            cfg.numAttrs = 2;
+        }
         void *args[] = {&ga};
         CK(cudaLaunchKernelExC(&cfg, v.kernel, args));
         g_launches.fetch_add(1, std::memory_order_relaxed);

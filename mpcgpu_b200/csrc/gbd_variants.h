@@ -19,15 +19,16 @@ namespace gbdlib {
 //      10 = v4 timeline build, 14 = v2 timeline build (%clock stamps of iterations 8..11 into gbd_pcg_set_debug_buffer())
 //   tolerance-parity family (GBD_PCG_NUMERICS_FAST; include/gbd/gbd_cluster_pcg_fast.cuh):
 //      20 = fast cluster kernel (single-exchange recurrence, per-CTA reductions), 1 CTA/SM; 21 = 2 CTAs/SM budget;
-//      22 = its timeline build; 24 = fast grid kernel (n = 64: whole GPU on one system)
+//      22 = its timeline build; 24 = fast grid kernel (n = 64: whole GPU on one system); 25 = the same with a two-level exchange
+//           (4-CTA clusters: DSMEM inside, L2 between the cluster leaders)
 //      26 = fast cluster kernel with packed knot rows (n lanes per row, 16 or 32 rows per CTA): the batch kernels
 //      27 = fast batch kernel (gbd_cluster_pcg_fastb.cuh: four rows of one matrix per thread, P-threads / S-threads), 1 CTA/SM;
 //      28 = the same, 2 CTAs/SM; 29 = its timeline build
-constexpr int MODE_GRID = 4, MODE_FAST = 20, MODE_FAST2 = 21, MODE_FAST_PROF = 22, MODE_FAST_GRID = 24, MODE_FAST_BATCH = 26,
+constexpr int MODE_GRID = 4, MODE_FAST = 20, MODE_FAST2 = 21, MODE_FAST_PROF = 22, MODE_FAST_GRID = 24, MODE_FAST_GRID2 = 25, MODE_FAST_BATCH = 26,
               MODE_FAST_B = 27, MODE_FAST_B2 = 28, MODE_FAST_B_PROF = 29;
 inline bool mode_is_packed(int mode) { return mode >= 26 && mode <= 28; }   // per-CTA products parked n per knot row (oracle: lanes = n)
 inline bool mode_is_fast(int mode) { return mode >= 20; }
-inline bool mode_is_grid(int mode) { return mode == MODE_GRID || mode == MODE_FAST_GRID; }
+inline bool mode_is_grid(int mode) { return mode == MODE_GRID || mode == MODE_FAST_GRID || mode == MODE_FAST_GRID2; }
 
 struct Variant {
     uint32_t n, N, C;
@@ -38,6 +39,7 @@ struct Variant {
     const void *kernel;
     const char *name;        // kernel family as it appears in profiles (ncu prints the full template name)
     size_t ws_words = 0;     // grid kernels: u64 words of packet workspace
+    uint32_t grid_cluster = 0;   // grid kernels: CTAs per thread-block cluster (0 / 1: launched without clusters)
     bool prepared = false;
     int resident = -1;       // cluster kernels: clusters of this shape the device can hold (set by prepare)
     bool unusable = false;   // the device cannot place even one cluster of this size: defaults skip the variant

@@ -36,7 +36,7 @@ def test_abi_version_and_variants(capi):
     # IIWA horizons of the reference (include/common/settings.cuh:123-138) + the GBD-PCG demo size
     assert {(14, 32), (14, 64), (14, 128), (14, 256), (14, 512), (2, 3)} <= pairs
     for v in vs:
-        assert v["N"] % v["cluster"] == 0 and 1 <= v["cluster"] <= (148 if v["mode"] in (4, 24) else 16)
+        assert v["N"] % v["cluster"] == 0 and 1 <= v["cluster"] <= (148 if v["mode"] in (4, 24, 25) else 16)
         assert v["threads"] % 32 == 0 and v["threads"] <= 1024
         assert v["smem"] <= 227 * 1024
     L = capi.lib()
