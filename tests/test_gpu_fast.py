@@ -141,6 +141,27 @@ def test_golden_iiwa_systems_tolerance_parity_vs_reference_kernel(torch_cuda, ca
     assert checked >= 8
 
 
+def test_config5_grid_kernel_tolerance_parity(torch_cuda, capi, oracle_pcg):
+    """BASELINE config 5 (n = 64, N = 256, tol 1e-6, cap 200): the default launch is the tolerance-parity grid kernel
+    (gbd_grid_pcg_fast.cuh); policy of SURVEY.md 8(c)(ii) against the unmodified reference kernel on this GPU (else the oracle)."""
+    import mpcgpu_b200 as m
+    from oracle import refgpu
+    torch = torch_cuda
+    n, N, cap, tol = 64, 256, 200, 1e-6
+    v = capi.resolved_variant(n, N)
+    assert v["fast"] and v["mode"] == 24, v
+    d = synth.make_systems(n, N, batch=1, seed=4242, nan_pads=True)
+    S, P, g, l0 = (d[k][0] for k in ("S", "Pinv", "gamma", "lambda0"))
+    got = _gpu_solve(torch, m, S, P, g, l0, n, N, cap, tol)
+    assert not got["max_iter_exit"] and np.isfinite(got["lam"]).all()
+    if refgpu.available():
+        rk = refgpu.solve(n, N, _dev(torch, S), _dev(torch, P), _dev(torch, g), _dev(torch, l0), cap, tol, block=128)
+        ref = dict(lam=rk["lam"].cpu().numpy(), iters=rk["iters"], max_iter_exit=rk["max_iter_exit"])
+    else:
+        ref = oracle_pcg.pcg(S, P, g, l0, n, N, cap, tol)
+    _assert_parity(oracle_pcg, got, ref, S, g, n, N, cap, "config 5 vs reference")
+
+
 @pytest.mark.parametrize("n,N,cap,tol", [(14, 32, 173, 1e-6), (14, 64, 167, 1e-5), (14, 128, 167, 1e-4), (14, 128, 167, 1e-6),
                                          (14, 256, 118, 1e-5), (6, 12, 60, 1e-6)])
 def test_synthetic_rings_tolerance_parity(torch_cuda, capi, oracle_pcg, n, N, cap, tol):
