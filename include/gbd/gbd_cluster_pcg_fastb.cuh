@@ -27,11 +27,16 @@
 // product: they compute the two near-halo rows of u from the Pinv tiles left in the staging buffer (same chain order).
 // The CPU restatement of this operation order is oracle/pcg_fast_oracle.c with G = 0.
 #pragma once
+#include <type_traits>
 #include "gbd_cluster_pcg_fast.cuh"
 
 namespace gbd {
 
-template <uint32_t n, uint32_t N, uint32_t C>
+// UX = true: the near-halo rows of u are not recomputed by this CTA (three lanes per element from staged Pinv tiles) but TRAVEL from the
+// neighbours that own them -- 16-byte {value, epoch, value, epoch} pair packets straight into the consumer's shared memory, read by
+// the four S-threads of the boundary row directly as their window pairs, in the tile they multiply LAST, so the hop hides behind the
+// two tiles that only need this CTA's rows.  Then only ONE redundant row of r / s each side is kept and one boundary row of w travels.
+template <uint32_t n, uint32_t N, uint32_t C, bool UX = false>
 struct ClusterPcgFastB {
     using T = float;
     static_assert(n >= 2 && n <= 16 && n % 2 == 0, "rows are held as n/2 register pairs per tile");
@@ -45,7 +50,8 @@ struct ClusterPcgFastB {
     static_assert(NT <= 1024 && 2 * n <= 32, "too many knot rows per CTA");
     static constexpr uint32_t SW0 = NP / 32;             // first S-warp: its lanes 0 .. 2n-1 also own the halo rows; also warps per role
     static_assert(SW0 <= 4, "the warp sums of a role are read with one 128-bit load");
-    static constexpr bool SPLIT3 = C > 1 && SW0 * 10 >= 2 * n;   // near-halo u by three lanes per element (needs 3 x 2n lanes in the S-warps)
+    static constexpr bool SPLIT3 = !UX && C > 1 && SW0 * 10 >= 2 * n;   // near-halo u by three lanes per element (needs 3 x 2n lanes in the S-warps)
+    static_assert(!UX || R >= 16, "u travels: the first and the last S-warp each hold ONE boundary row");
     static constexpr uint32_t TILE = 3 * n * n;
     static constexpr bool TMA_OK = (TILE * sizeof(T)) % 16 == 0;
     static constexpr uint32_t HALO_PAR = 2 * 2 * XS;     // halo packets per parity: [side][slot][XS]
@@ -57,7 +63,8 @@ struct ClusterPcgFastB {
     static constexpr size_t OFF_RU = OFF_DOT + 2 * C * 16;                  // [4] r.u sums of the P-warps
     static constexpr size_t OFF_WU = OFF_RU + 16;                           // [4] w.u sums of the S-warps
     static constexpr size_t OFF_HALO = OFF_WU + 16;                         // [2][2][2][XS] x 8 B  w boundary rows from the neighbours
-    static constexpr size_t OFF_XL = OFF_HALO + 2 * HALO_PAR * 8;           // lambda0 rows a-3 .. a+R+2 (prologue only)
+    static constexpr size_t OFF_UH = OFF_HALO + 2 * HALO_PAR * 8;           // UX: [2][2 sides][8] x 16 B  pair packets of the neighbours' boundary rows of u
+    static constexpr size_t OFF_XL = OFF_UH + 2 * 2 * 8 * 16;               // lambda0 rows a-3 .. a+R+2 (prologue only)
     static constexpr size_t OFF_XR = OFF_XL + sizeof(T) * (R + 6) * XS;     // r rows a-2 .. a+R+1
     static constexpr size_t OFF_XU = OFF_XR + sizeof(T) * (R + 4) * XS;     // u rows a-1 .. a+R
     static constexpr size_t OFF_S = OFF_XU + sizeof(T) * (R + 2) * XS;      // S rows a-2 .. a+R+1 (staging)
@@ -123,10 +130,10 @@ __device__ __forceinline__ float chain_smem_row(uint32_t tile_row, uint32_t xw, 
     return __fadd_rn(__fadd_rn(__fadd_rn(lo[0], lo[1]), lo[2]), __fadd_rn(__fadd_rn(hi[0], hi[1]), hi[2]));
 }
 
-template <uint32_t n, uint32_t N, uint32_t C>
+template <uint32_t n, uint32_t N, uint32_t C, bool UX = false>
 __device__ __forceinline__ void pcg_cluster_fastb_init(unsigned char *smem_raw)
 {
-    using K = ClusterPcgFastB<n, N, C>;
+    using K = ClusterPcgFastB<n, N, C, UX>;
     uint32_t *z = reinterpret_cast<uint32_t *>(smem_raw);
     for (uint32_t i = threadIdx.x; i < K::OFF_XL / 4; i += blockDim.x) z[i] = 0u;       // epoch 0 is never sent
     __syncthreads();
@@ -136,10 +143,10 @@ __device__ __forceinline__ void pcg_cluster_fastb_init(unsigned char *smem_raw)
     }
 }
 
-template <uint32_t n, uint32_t N, uint32_t C, bool PROF = false>
+template <uint32_t n, uint32_t N, uint32_t C, bool PROF = false, bool UX = false>
 __device__ __forceinline__ void pcg_cluster_fastb_run(const PcgArgs<float> &a, unsigned char *smem_raw, uint32_t first_sys, uint32_t sys_stride)
 {
-    using K = ClusterPcgFastB<n, N, C>;
+    using K = ClusterPcgFastB<n, N, C, UX>;
     constexpr uint32_t R = K::R, TILE = K::TILE, XS = K::XS, NT = K::NT, NP = K::NP, H = K::H, RPT = K::RPT, Q = K::Q, NW = K::SW0;
     constexpr unsigned FULL = 0xffffffffu;
     constexpr uint32_t ROWB = 4u * XS;                         // bytes of one window row
@@ -198,7 +205,19 @@ __device__ __forceinline__ void pcg_cluster_fastb_run(const PcgArgs<float> &a, u
     const uint32_t win_r = opaque(sb + (uint32_t)K::OFF_XR + (g + 1) * ROWB), win_u = win_r + U_MINUS_R;
     // S-threads of the boundary rows send w: own rows 0, 1 to the left neighbour's right-side slots 0 (near), 1 (far); rows R-1, R-2
     // to the right neighbour's left-side slots 0, 1.  Generic pointers into the peers' shared memory, formed once.
-    const bool send_l = !isP && has_left && g < 2, send_r = !isP && has_right && g + 2 >= R;
+    constexpr uint32_t HROWS = UX ? 1u : 2u;                   // boundary rows of w that travel each way
+    const bool send_l = !isP && has_left && g < HROWS, send_r = !isP && has_right && g + HROWS >= R;
+    // UX: the P-threads of the first / last own row send u; the S-threads of those rows read the neighbour's u from packets
+    const bool usend_l = UX && isP && has_left && g == 0, usend_r = UX && isP && has_right && g + 1 == R;
+    const bool upk = UX && !isP && ((g == 0 && has_left) || (g + 1 == R && has_right));
+    const uint32_t ublk_pk = g == 0 ? 0u : 2u;                 // the tile whose window comes from packets
+    const uint32_t uh_u = sb + (uint32_t)K::OFF_UH;
+    uint64_t gaddr_u = 0;
+    uint32_t my_uh = 0;
+    if constexpr (UX) {
+        gaddr_u = opaque(cluster_generic(map_to_cta(uh_u, usend_l ? cr - 1 : (usend_r ? cr + 1 : cr)) + 16u * ((usend_l ? 8u : 0u) + q)));
+        my_uh = opaque(uh_u + 16u * (g == 0 ? 0u : 8u));         // side 0 = from the left neighbour, side 1 = from the right
+    }
     const uint32_t halo_u = sb + (uint32_t)K::OFF_HALO, dot_u = opaque(sb + (uint32_t)K::OFF_DOT), next_u = sb + (uint32_t)K::OFF_NEXT;
     const uint64_t gaddr_l = opaque(cluster_generic(map_to_cta(halo_u, send_l ? cr - 1 : cr) + 8u * ((2u + (g & 1u)) * XS + q)));
     const uint64_t gaddr_r = opaque(cluster_generic(map_to_cta(halo_u, send_r ? cr + 1 : cr) + 8u * (((R - 1 - g) & 1u) * XS + q)));
@@ -328,7 +347,8 @@ __device__ __forceinline__ void pcg_cluster_fastb_run(const PcgArgs<float> &a, u
         }
         if (hl) {
             hr = __fsub_rn(hrhs, chain_smem_row<n, N, XS>(sb + (uint32_t)K::OFF_S + hrow_xr * TILE * 4u, sb + (uint32_t)K::OFF_XL + hrow_xr * ROWB, hb, hj));
-            hr2 = __fsub_rn(hrhs2, chain_smem_row<n, N, XS>(sb + (uint32_t)K::OFF_S + hfar_xr * TILE * 4u, sb + (uint32_t)K::OFF_XL + hfar_xr * ROWB, hb2, hj));
+            if constexpr (!UX)
+                hr2 = __fsub_rn(hrhs2, chain_smem_row<n, N, XS>(sb + (uint32_t)K::OFF_S + hfar_xr * TILE * 4u, sb + (uint32_t)K::OFF_XL + hfar_xr * ROWB, hb2, hj));
         }
         float alpha = 0.f, beta = 0.f;
         float gam = 0.f, den = 0.f;                              // exchange warp: current gamma and CG denominator
@@ -343,7 +363,7 @@ __device__ __forceinline__ void pcg_cluster_fastb_run(const PcgArgs<float> &a, u
                 }
                 if (hl) {
                     sts_f32(h_xr, hr);
-                    sts_f32(h_xr2, hr2);
+                    if constexpr (!UX) sts_f32(h_xr2, hr2);
                 }
             }
             __syncthreads();
@@ -358,6 +378,17 @@ __device__ __forceinline__ void pcg_cluster_fastb_run(const PcgArgs<float> &a, u
                 if (pair0) sts_f32x2(a_own_r + U_MINUS_R, out[0], out[1]);
                 if constexpr (RPT > 2) {
                     if (pair1) sts_f32x2(a_own_r + U_MINUS_R + 32u, out[2], out[3]);
+                }
+                if constexpr (UX) {
+                    if (usend_l || usend_r) {                        // this row of u is the neighbour's near-halo row: pair q, and pair q + 4
+                        const uint64_t ga = gaddr_u + 256u * par;
+                        if (pair0)
+                            asm volatile("st.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(ga), "r"(__float_as_uint(out[0])), "r"(ep), "r"(__float_as_uint(out[1])), "r"(ep) : "memory");
+                        if constexpr (RPT > 2) {
+                            if (pair1)
+                                asm volatile("st.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(ga + 64u), "r"(__float_as_uint(out[2])), "r"(ep), "r"(__float_as_uint(out[3])), "r"(ep) : "memory");
+                        }
+                    }
                 }
             } else if constexpr (K::SPLIT3) {
                 // ---- u on the two near halo rows (their Pinv tiles are still in the staging buffer): three lanes per element, one
@@ -387,7 +418,61 @@ __device__ __forceinline__ void pcg_cluster_fastb_run(const PcgArgs<float> &a, u
             if (!isP) {
                 // ---- w = S u on the own rows; the w.u products parked; boundary rows sent to the neighbours
                 stamp(14, v2[0]);
-                chain_pairs_multi<n, XS, RPT>(mm, win_u, out);
+                if constexpr (UX) {
+                    // tile by tile: the first S-warp (it holds own row 0) multiplies its LEFT tile last, the others their right tile, so
+                    // that the neighbour's row of u -- read from its packets by the four threads of the boundary row -- has time to arrive
+                    f32x2 acc[RPT][3];
+                    auto do_tile = [&](auto BLK) {
+                        constexpr uint32_t blk = decltype(BLK)::value;
+                        f32x2 x[(H + 1) / 2 * 2];
+                        if (upk && ublk_pk == blk) {
+                            bool ok;
+                            SpinGuard guard;
+                            do {
+                                guard.tick();
+                                ok = true;
+#pragma unroll
+                                for (uint32_t c = 0; c < H; ++c) {
+                                    const uint4 q4 = ld_pair(my_uh + 256u * par + 16u * c);
+                                    ok = ok && q4.y == ep && q4.w == ep;
+                                    x[c] = pack2(__uint_as_float(q4.x), __uint_as_float(q4.z));
+                                }
+                            } while (!ok);
+                            if constexpr (H % 2 == 1) x[H] = 0ull;
+                        } else {
+#pragma unroll
+                            for (uint32_t qq = 0; qq < (H + 1) / 2; ++qq) {
+                                const float4 f = lds_f32x4(win_u + 4u * (blk * XS + 4u * qq));
+                                x[2 * qq] = pack2(f.x, f.y);
+                                x[2 * qq + 1] = pack2(f.z, f.w);
+                            }
+                        }
+#pragma unroll
+                        for (uint32_t k = 0; k < RPT; ++k) {
+                            f32x2 sacc = mul2(mm[(k * 3 + blk) * H], x[0]);
+#pragma unroll
+                            for (uint32_t c = 1; c < H; ++c) sacc = fma2(mm[(k * 3 + blk) * H + c], x[c], sacc);
+                            acc[k][blk] = sacc;
+                        }
+                    };
+                    if (warp == NW) {
+                        do_tile(std::integral_constant<uint32_t, 1>{});
+                        do_tile(std::integral_constant<uint32_t, 2>{});
+                        do_tile(std::integral_constant<uint32_t, 0>{});
+                    } else {
+                        do_tile(std::integral_constant<uint32_t, 0>{});
+                        do_tile(std::integral_constant<uint32_t, 1>{});
+                        do_tile(std::integral_constant<uint32_t, 2>{});
+                    }
+#pragma unroll
+                    for (uint32_t k = 0; k < RPT; ++k) {
+                        float lo, hi;
+                        unpack2(add2(add2(acc[k][0], acc[k][1]), acc[k][2]), lo, hi);
+                        out[k] = __fadd_rn(lo, hi);
+                    }
+                } else {
+                    chain_pairs_multi<n, XS, RPT>(mm, win_u, out);
+                }
                 stamp(15, out[0] + out[1]);
                 const float wsum = warp_sum(own_products(a_own_r + U_MINUS_R, out));
                 if (lane == 0) sts_f32(a_wu + 4u * (warp - NW), wsum);
@@ -405,7 +490,7 @@ __device__ __forceinline__ void pcg_cluster_fastb_run(const PcgArgs<float> &a, u
                 }
                 if (hl) {                                            // first touch of the slots now: a slot is seen sooner once polled
                     k0 = ld_packet_local(my_halo + par * HALO_PAR_BYTES);
-                    k1 = ld_packet_local(my_halo + par * HALO_PAR_BYTES + 8u * XS);
+                    if constexpr (!UX) k1 = ld_packet_local(my_halo + par * HALO_PAR_BYTES + 8u * XS);
                 }
                 stamp(5, out[0]);
             } else if (!xw) {
@@ -481,13 +566,13 @@ __device__ __forceinline__ void pcg_cluster_fastb_run(const PcgArgs<float> &a, u
                 done = lds_f32(a_sc + 8u) != 0.f;
                 if (hl) {
                     uint32_t spins2 = 0;
-                    while (!(packet_ok(k0, ep) && packet_ok(k1, ep))) {
+                    while (!(packet_ok(k0, ep) && (UX || packet_ok(k1, ep)))) {
                         k0 = ld_packet_local(my_halo + par * HALO_PAR_BYTES);
-                        k1 = ld_packet_local(my_halo + par * HALO_PAR_BYTES + 8u * XS);
+                        if constexpr (!UX) k1 = ld_packet_local(my_halo + par * HALO_PAR_BYTES + 8u * XS);
                         if (++spins2 > (1u << 24)) __trap();          // a lost packet is an error (launch failure), not a hang
                     }
                     hw = packet_val(k0);
-                    hw2 = packet_val(k1);
+                    if constexpr (!UX) hw2 = packet_val(k1);
                 }
                 stamp(10, hw);
             }
@@ -517,8 +602,10 @@ __device__ __forceinline__ void pcg_cluster_fastb_run(const PcgArgs<float> &a, u
             }
             hs = __fmaf_rn(beta, hs, hw);
             hr = __fmaf_rn(-alpha, hs, hr);
-            hs2 = __fmaf_rn(beta, hs2, hw2);
-            hr2 = __fmaf_rn(-alpha, hs2, hr2);
+            if constexpr (!UX) {
+                hs2 = __fmaf_rn(beta, hs2, hw2);
+                hr2 = __fmaf_rn(-alpha, hs2, hr2);
+            }
             step();
             stamp(11, alpha);
             if (done) { ++iter; max_iter_exit = 0; break; }
@@ -559,15 +646,15 @@ __device__ __forceinline__ void pcg_cluster_fastb_run(const PcgArgs<float> &a, u
 }
 
 // C-ABI kernel: persistent clusters looping over a batch of systems
-template <uint32_t n, uint32_t N, uint32_t C, uint32_t MINB, bool PROF = false>
-__global__ void __launch_bounds__(ClusterPcgFastB<n, N, C>::NT, MINB)
+template <uint32_t n, uint32_t N, uint32_t C, uint32_t MINB, bool PROF = false, bool UX = false>
+__global__ void __launch_bounds__(ClusterPcgFastB<n, N, C, UX>::NT, MINB)
 pcg_cluster_kernel_fastb(const PcgArgs<float> a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    pcg_cluster_fastb_init<n, N, C>(smem_raw);
+    pcg_cluster_fastb_init<n, N, C, UX>(smem_raw);
     __syncthreads();
     cluster_sync();   // all CTAs resident, packet buffers cleared, before any DSMEM traffic
-    pcg_cluster_fastb_run<n, N, C, PROF>(a, smem_raw, cluster_idx(), cluster_count());
+    pcg_cluster_fastb_run<n, N, C, PROF, UX>(a, smem_raw, cluster_idx(), cluster_count());
     cluster_sync();   // no CTA leaves while a peer may still write into its shared memory
 }
 

@@ -23,10 +23,10 @@ namespace gbdlib {
 //           (4-CTA clusters: DSMEM inside, L2 between the cluster leaders)
 //      26 = fast cluster kernel with packed knot rows (n lanes per row, 16 or 32 rows per CTA): the batch kernels
 //      27 = fast batch kernel (gbd_cluster_pcg_fastb.cuh: four rows of one matrix per thread, P-threads / S-threads), 1 CTA/SM;
-//      28 = the same, 2 CTAs/SM; 29 = its timeline build
+//      28 = the same, 2 CTAs/SM; 29 = its timeline build; 31 = the same with the near-halo rows of u travelling instead of recomputed
 constexpr int MODE_GRID = 4, MODE_FAST = 20, MODE_FAST2 = 21, MODE_FAST_PROF = 22, MODE_FAST_GRID = 24, MODE_FAST_GRID2 = 25, MODE_FAST_BATCH = 26,
-              MODE_FAST_B = 27, MODE_FAST_B2 = 28, MODE_FAST_B_PROF = 29;
-inline bool mode_is_packed(int mode) { return mode >= 26 && mode <= 28; }   // per-CTA products parked n per knot row (oracle: lanes = n)
+              MODE_FAST_B = 27, MODE_FAST_B2 = 28, MODE_FAST_B_PROF = 29, MODE_FAST_BX = 31;
+inline bool mode_is_packed(int mode) { return (mode >= 26 && mode <= 28) || mode == 31; }   // per-CTA products parked n per knot row (oracle: lanes = n)
 inline bool mode_is_fast(int mode) { return mode >= 20; }
 inline bool mode_is_grid(int mode) { return mode == MODE_GRID || mode == MODE_FAST_GRID || mode == MODE_FAST_GRID2; }
 

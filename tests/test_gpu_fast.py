@@ -94,10 +94,10 @@ def test_every_fast_variant_bit_exact_vs_its_own_oracle(torch_cuda, capi, oracle
     L = capi.lib()
     seen = 0
     for v in capi.variants():
-        if not v["fast"] or v["mode"] not in (20, 21, 24, 25, 26, 27, 28):
+        if not v["fast"] or v["mode"] not in (20, 21, 24, 25, 26, 27, 28, 31):
             continue
         n, N, C = v["n"], v["N"], v["cluster"]
-        lanes = {24: 1, 25: 1, 26: n, 27: 0, 28: 0}.get(v["mode"], 16)  # the oracle's reduction order: 16 / n lanes per knot row, 0 = batch kernel, 1 = grid kernel
+        lanes = {24: 1, 25: 1, 26: n, 27: 0, 28: 0, 31: 0}.get(v["mode"], 16)  # the oracle's reduction order: 16 / n lanes per knot row, 0 = batch kernel, 1 = grid kernel
         d = synth.make_systems(n, N, batch=2, seed=300 + n + N, nan_pads=True)
         cap, tol = (40, 1e-7) if N > 128 else (60, 1e-6)
         if n == 64 and N == 256:
