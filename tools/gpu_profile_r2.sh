@@ -11,5 +11,7 @@ timeout -k 5 600 ncu --set full --clock-control none --import-source on -k regex
    -f -o gpurun_out/prof_r02_single32 env BATCH=1 KNOTS=32 CAP=173 python tools/one_solve.py > gpurun_out/prof_r02_single32.log 2>&1
 timeout -k 5 600 ncu --set full --clock-control none --import-source on -k regex:fastb -s 1 -c 1 \
    -f -o gpurun_out/prof_r02_batched256 env BATCH=256 SINGLES=0 KNOTS=128 python tools/one_solve.py > gpurun_out/prof_r02_batched256.log 2>&1
+timeout -k 5 600 ncu --set full --clock-control none --import-source on -k regex:pcg_grid_kernel_fast -s 3 -c 1 \
+   -f -o gpurun_out/prof_r02_cfg5 env BATCH=1 STATE=64 KNOTS=256 CAP=200 TOL=1e-6 SINGLES=6 python tools/one_solve.py > gpurun_out/prof_r02_cfg5.log 2>&1
 ls -la gpurun_out/*.ncu-rep gpurun_out/r02_launches_bench.csv
-for f in single128 single32 batched256; do tail -n 2 gpurun_out/prof_r02_$f.log; done
+for f in single128 single32 batched256 cfg5; do tail -n 2 gpurun_out/prof_r02_$f.log; done

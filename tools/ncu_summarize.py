@@ -37,7 +37,8 @@ summary = {"round": 2, "how": "ncu --set full --clock-control none --import-sour
            "kernels": []}
 for name, extra in (("single128", {"workload": "one solve n=14 N=128 (synthetic ring of tools/one_solve.py), default numerics"}),
                     ("single32", {"workload": "one solve n=14 N=32, default numerics"}),
-                    ("batched256", {"workload": "256 systems n=14 N=128 in one launch, default numerics", "systems": 256})):
+                    ("batched256", {"workload": "256 systems n=14 N=128 in one launch, default numerics", "systems": 256}),
+                    ("cfg5", {"workload": "one solve n=64 N=256 (BASELINE config 5), default numerics: the tolerance-parity grid kernel"})):
     rep = os.path.join(OUT, f"prof_r02_{name}.ncu-rep")
     if not os.path.exists(rep):
         continue
