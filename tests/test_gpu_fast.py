@@ -181,22 +181,29 @@ def test_synthetic_rings_tolerance_parity(torch_cuda, capi, oracle_pcg, n, N, ca
             _assert_parity(oracle_pcg, got, rk, S, g, n, N, cap, f"({n},{N}) vs reference kernel")
 
 
-def test_exit_semantics_and_warm_start(torch_cuda, capi, oracle_pcg):
-    """pcg.cuh:195,212: iters = k+1 when iteration k passed the test, max_iter with the flag set otherwise; lambda is in/out."""
+@pytest.mark.parametrize("n,N,C,mode", [(14, 32, 4, 20), (14, 32, 1, 27), (14, 64, 2, 27), (14, 128, 4, 31), (32, 8, 4, 24), (32, 32, 16, 25)])
+def test_exit_semantics_and_warm_start(torch_cuda, capi, oracle_pcg, n, N, C, mode):
+    """pcg.cuh:195,212: iters = k+1 when iteration k passed the test, max_iter with the flag set otherwise; lambda is in/out.
+    One kernel of every tolerance-parity family: single-solve, batch (one CTA per system, 2- and 4-CTA clusters), grid (flat and
+    two-level exchange)."""
     import mpcgpu_b200 as m
-    n, N = 14, 32
-    C = capi.resolved_variant(n, N)["cluster"]
+    lanes = {24: 1, 25: 1, 26: n, 27: 0, 28: 0, 31: 0}.get(mode, 16)
     d = synth.make_systems(n, N, seed=21)
     S, P, g, l0 = (d[k][0] for k in ("S", "Pinv", "gamma", "lambda0"))
-    for cap, tol in ((3, 1e-30), (0, 1e-6), (50, 1e30), (1, 1e-30)):
-        got = _gpu_solve(torch_cuda, m, S, P, g, l0, n, N, cap, tol)
-        ref = oracle_pcg.pcg(S, P, g, l0, n, N, cap, tol)
-        assert (got["iters"], got["max_iter_exit"]) == (ref["iters"], ref["max_iter_exit"])
-        _assert_same(got, oracle_pcg.pcg_fast(S, P, g, l0, n, N, C, cap, tol), f"cap {cap} tol {tol}")
-    full = _gpu_solve(torch_cuda, m, S, P, g, l0, n, N, 173, 1e-7)
-    warm = _gpu_solve(torch_cuda, m, S, P, g, full["lam"], n, N, 173, 1e-7)
-    assert warm["iters"] < full["iters"]
-    _assert_same(warm, oracle_pcg.pcg_fast(S, P, g, full["lam"], n, N, C, 173, 1e-7), "warm start")
+    big = 173
+    assert capi.lib().gbd_pcg_set_tuning(n, N, 0, C, mode) == 0
+    try:
+        for cap, tol in ((3, 1e-30), (0, 1e-6), (50, 1e30), (1, 1e-30)):
+            got = _gpu_solve(torch_cuda, m, S, P, g, l0, n, N, cap, tol)
+            ref = oracle_pcg.pcg(S, P, g, l0, n, N, cap, tol)
+            assert (got["iters"], got["max_iter_exit"]) == (ref["iters"], ref["max_iter_exit"])
+            _assert_same(got, oracle_pcg.pcg_fast(S, P, g, l0, n, N, C, cap, tol, lanes=lanes), f"cap {cap} tol {tol}")
+        full = _gpu_solve(torch_cuda, m, S, P, g, l0, n, N, big, 1e-7)
+        warm = _gpu_solve(torch_cuda, m, S, P, g, full["lam"], n, N, big, 1e-7)
+        assert warm["iters"] < full["iters"]
+        _assert_same(warm, oracle_pcg.pcg_fast(S, P, g, full["lam"], n, N, C, big, 1e-7, lanes=lanes), "warm start")
+    finally:
+        capi.lib().gbd_pcg_set_tuning(n, N, 0, 0, -1)
 
 
 @pytest.mark.parametrize("C,mode", [(2, 20), (2, 26), (1, 27), (2, 28)])
