@@ -297,3 +297,37 @@ def test_dropin_headers_fast_body_reference_launch_geometry(torch_cuda, oracle_p
     else:
         want = oracle_pcg.pcg(d["S"][0], d["Pinv"][0], d["gamma"][0], d["lambda0"][0], n, knots, cap, tol)
     _assert_same(got, want, f"fast drop-in N={knots} block={block}")
+
+
+@pytest.mark.parametrize("n,N,C,mode,batch", [(14, 32, 4, 20, 1), (14, 32, 1, 27, 5), (14, 64, 2, 27, 3), (32, 8, 4, 24, 1)])
+def test_unaligned_pointers_take_the_non_tma_path(torch_cuda, capi, oracle_pcg, n, N, C, mode, batch):
+    """S / Pinv that are only 4-byte aligned cannot be staged by TMA bulk copies: every tolerance-parity family falls back to plain
+    loads and still equals its oracle bit for bit."""
+    import mpcgpu_b200 as m
+    torch = torch_cuda
+    lanes = {24: 1, 25: 1, 26: n, 27: 0, 28: 0, 31: 0}.get(mode, 16)
+    cap, tol = 50, 1e-6
+    d = synth.make_systems(n, N, batch=batch, seed=17)
+    mat = 3 * n * n * N
+    bigS, bigP = torch.zeros(batch * mat + 1, device="cuda"), torch.zeros(batch * mat + 1, device="cuda")
+    S, P = bigS[1:], bigP[1:]                                 # 4-byte aligned only
+    S.copy_(_dev(torch, d["S"]).reshape(-1))
+    P.copy_(_dev(torch, d["Pinv"]).reshape(-1))
+    assert S.data_ptr() % 16 != 0 and P.data_ptr() % 16 != 0
+    g, lam = _dev(torch, d["gamma"]).reshape(-1), _dev(torch, d["lambda0"]).reshape(-1)
+    it = torch.zeros(batch, dtype=torch.int32, device="cuda")
+    fl = torch.zeros(batch, dtype=torch.uint8, device="cuda")
+    assert capi.lib().gbd_pcg_set_tuning(n, N, 0, C, mode) == 0
+    try:
+        if batch == 1:
+            m.pcg_launch(n, N, S, P, g, lam, None, None, None, None, it, fl, cap, tol)
+        else:
+            m.solve_batched(n, N, batch, S, P, g, lam, it, fl, cap, tol)
+        torch.cuda.synchronize()
+    finally:
+        capi.lib().gbd_pcg_set_tuning(n, N, 0, 0, -1)
+    lam = lam.cpu().numpy().reshape(batch, n * N)
+    for i in range(batch):
+        want = oracle_pcg.pcg_fast(d["S"][i], d["Pinv"][i], d["gamma"][i], d["lambda0"][i], n, N, C, cap, tol, lanes=lanes)
+        assert int(it[i]) == want["iters"] and bool(fl[i]) == want["max_iter_exit"], i
+        assert np.array_equal(lam[i], want["lam"]), i
