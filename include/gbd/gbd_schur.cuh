@@ -86,8 +86,20 @@ __device__ __forceinline__ void gj_regs(float (&a)[2 * DIM], float *snap, uint32
         const float q = __fdiv_rn(num, piv);
         if (lane >= 16 && lane - 16 <= DIM) nrow[cI] = q;
         __syncwarp();
+        // lane p takes the new pivot row, every other lane the old one: one address select, then 128-bit loads (the
+        // snapshots are 16 floats each; entries past DIM are never used)
+        constexpr uint32_t NV4 = (DIM + 4) / 4;
+        const float4 *src = reinterpret_cast<const float4 *>(lane == p ? nrow : row);
 #pragma unroll
-        for (uint32_t c = 0; c <= DIM; ++c) a[p + c] = (lane == p) ? nrow[c] : fma_(-q, row[c], a[p + c]);
+        for (uint32_t i = 0; i < NV4; ++i) {
+            const float4 f = src[i];
+            const float v[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+            for (uint32_t e = 0; e < 4; ++e) {
+                const uint32_t c = 4 * i + e;
+                if (c <= DIM) a[p + c] = (lane == p) ? v[e] : fma_(-q, v[e], a[p + c]);
+            }
+        }
         __syncwarp();
     }
 }
@@ -130,6 +142,68 @@ __device__ __forceinline__ float matvec_elem(const float *mat, const float *vec,
     for (uint32_t c = 0; c < COLS; ++c) res = fma_(mat[row + c * ROWS], vec[c], res);
     return res;
 }
+// Register-blocked forms of the two helpers above for even M: the rows (r, r+1), r even, of a column-major operand are one
+// 64-bit shared-memory load.  Every output element is still one FMA per term in ascending k from 0.0f -> the same bits as
+// gemm_elem / matvec_elem; what changes is the instruction count (the batched assembly is issue-bound): 2 x 2 outputs cost
+// 2 loads + 4 FMAs per k instead of 8 loads + 4 FMAs.
+// o = {(r, c), (r+1, c), (r, c+1), (r+1, c+1)} of A (M x K) * B (K x NC)  [TB: A * B^T, B stored NC x K]; r, c even
+template <uint32_t M, uint32_t K, uint32_t NC, bool TB>
+__device__ __forceinline__ void gemm_2x2(const float *A, const float *B, uint32_t r, uint32_t c, float (&o)[4])
+{
+    static_assert(M % 2 == 0 && NC % 2 == 0, "row pairs and column pairs");
+    o[0] = o[1] = o[2] = o[3] = 0.0f;
+    if constexpr (!TB && K % 2 == 0) {
+#pragma unroll
+        for (uint32_t k = 0; k < K; k += 2) {
+            const float2 a0 = *reinterpret_cast<const float2 *>(A + k * M + r), a1 = *reinterpret_cast<const float2 *>(A + (k + 1) * M + r);
+            const float2 b0 = *reinterpret_cast<const float2 *>(B + c * K + k), b1 = *reinterpret_cast<const float2 *>(B + (c + 1) * K + k);
+            o[0] = fma_(a0.x, b0.x, o[0]); o[0] = fma_(a1.x, b0.y, o[0]);
+            o[1] = fma_(a0.y, b0.x, o[1]); o[1] = fma_(a1.y, b0.y, o[1]);
+            o[2] = fma_(a0.x, b1.x, o[2]); o[2] = fma_(a1.x, b1.y, o[2]);
+            o[3] = fma_(a0.y, b1.x, o[3]); o[3] = fma_(a1.y, b1.y, o[3]);
+        }
+    } else {
+#pragma unroll
+        for (uint32_t k = 0; k < K; ++k) {
+            const float2 a = *reinterpret_cast<const float2 *>(A + k * M + r);
+            float b0, b1;
+            if constexpr (TB) {
+                const float2 bb = *reinterpret_cast<const float2 *>(B + k * NC + c);
+                b0 = bb.x; b1 = bb.y;
+            } else {
+                b0 = B[c * K + k]; b1 = B[(c + 1) * K + k];
+            }
+            o[0] = fma_(a.x, b0, o[0]); o[1] = fma_(a.y, b0, o[1]);
+            o[2] = fma_(a.x, b1, o[2]); o[3] = fma_(a.y, b1, o[3]);
+        }
+    }
+}
+// o = {(r, c), (r+1, c)} of A (M x K) * B (K x NC), r even
+template <uint32_t M, uint32_t K>
+__device__ __forceinline__ void gemm_2x1(const float *A, const float *B, uint32_t r, uint32_t c, float (&o)[2])
+{
+    static_assert(M % 2 == 0, "row pairs");
+    o[0] = o[1] = 0.0f;
+#pragma unroll
+    for (uint32_t k = 0; k < K; ++k) {
+        const float2 a = *reinterpret_cast<const float2 *>(A + k * M + r);
+        const float b = B[c * K + k];
+        o[0] = fma_(a.x, b, o[0]); o[1] = fma_(a.y, b, o[1]);
+    }
+}
+// o = rows (r, r+1) of mat (ROWS x COLS, column-major) * vec, r even
+template <uint32_t ROWS, uint32_t COLS>
+__device__ __forceinline__ void matvec_2(const float *mat, const float *vec, uint32_t r, float (&o)[2])
+{
+    static_assert(ROWS % 2 == 0, "row pairs");
+    o[0] = o[1] = 0.0f;
+#pragma unroll
+    for (uint32_t c = 0; c < COLS; ++c) {
+        const float2 a = *reinterpret_cast<const float2 *>(mat + c * ROWS + r);
+        const float x = vec[c];
+        o[0] = fma_(a.x, x, o[0]); o[1] = fma_(a.y, x, o[1]);
+    }
+}
 __device__ __forceinline__ void identity(float *A, uint32_t dim, uint32_t t, uint32_t nt)
 {
     for (uint32_t i = t; i < dim * dim; i += nt) A[i] = (i % dim == i / dim) ? 1.0f : 0.0f;
@@ -150,14 +224,15 @@ struct SchurShape {
 
 // ---- phase 1: one CTA per block row (linsys_setup.cuh:139-562)
 template <uint32_t n, uint32_t m>
-__global__ void __launch_bounds__(SchurShape<n, m>::NT)
+__global__ void __launch_bounds__(SchurShape<n, m>::NT, 8)
 schur_phase1_kernel(uint32_t N, const float *__restrict__ G, const float *__restrict__ C, const float *__restrict__ g,
                     const float *__restrict__ c, float *__restrict__ S, float *__restrict__ Pinv, float *__restrict__ gamma, float rho)
 {
     using namespace schur_detail;
     using K = SchurShape<n, m>;
     constexpr uint32_t nn = K::nn, mm = K::mm, nm = K::nm, NT = K::NT;
-    extern __shared__ float sm[];
+    static_assert(n % 2 == 0, "the blocked products pair the rows of column-major n x n operands");
+    extern __shared__ __align__(16) float sm[];
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // phase 2 may be scheduled; it waits for our completion
     float *sA = sm, *sB = sA + nn, *sQk = sB + nm, *sQk_i = sQk + nn, *sQp = sQk_i + nn, *sQp_i = sQp + nn;
     float *sR = sQp_i + nn, *sR_i = sR + mm, *sPhi = sR_i + mm, *sBR = sPhi + nn, *sTh = sBR + nm, *sTh_i = sTh + nn;
@@ -213,19 +288,61 @@ schur_phase1_kernel(uint32_t N, const float *__restrict__ G, const float *__rest
     for (uint32_t i = t; i < mm; i += NT) (Prow - 3 * nn)[2 * nn + i] = sR_i[i];
     if (b == N - 1)
         for (uint32_t i = t; i < nn; i += NT) Pinv[i] = sQp_i[i];
-    // ---- stage A: phi = A Q_k^-1, BR = B R_k^-1, gam = Q_kp1^-1 q_kp1  (:385-413)
-    for (uint32_t task = t; task < nn + nm + n; task += NT) {
-        if (task < nn) sPhi[task] = gemm_elem<false>(sA, sQk_i, n, n, n, task % n, task / n);
-        else if (task < nn + nm) { const uint32_t e = task - nn; sBR[e] = gemm_elem<false>(sB, sR_i, n, m, m, e % n, e / n); }
-        else { const uint32_t e = task - nn - nm; sgam[e] = matvec_elem(sQp_i, sqp, n, n, e); }
+    // ---- stage A: phi = A Q_k^-1, BR = B R_k^-1, gam = Q_kp1^-1 q_kp1  (:385-413).  Register-blocked tasks (2 x 2, 2 x 1, two
+    // rows); the task kinds start on warp boundaries (phi | BR, gam), so a stage is ONE pass over the CTA with two warps per kind
+    constexpr uint32_t HN = n / 2, T_SQ = HN * HN, S_SQ = (T_SQ + 31) / 32 * 32;
+    for (uint32_t slot = t; slot < S_SQ + HN * m + HN; slot += NT) {
+        if (slot < S_SQ) {
+            if (slot < T_SQ) {
+                const uint32_t r = 2 * (slot % HN), cc = 2 * (slot / HN);
+                float o[4];
+                gemm_2x2<n, n, n, false>(sA, sQk_i, r, cc, o);
+                *reinterpret_cast<float2 *>(sPhi + cc * n + r) = make_float2(o[0], o[1]);
+                *reinterpret_cast<float2 *>(sPhi + (cc + 1) * n + r) = make_float2(o[2], o[3]);
+            }
+        } else if (slot < S_SQ + HN * m) {
+            const uint32_t e = slot - S_SQ, r = 2 * (e % HN), cc = e / HN;
+            float o[2];
+            gemm_2x1<n, m>(sB, sR_i, r, cc, o);
+            *reinterpret_cast<float2 *>(sBR + cc * n + r) = make_float2(o[0], o[1]);
+        } else {
+            const uint32_t r = 2 * (slot - S_SQ - HN * m);
+            float o[2];
+            matvec_2<n, n>(sQp_i, sqp, r, o);
+            sgam[r] = o[0];
+            sgam[r + 1] = o[1];
+        }
     }
     __syncthreads();
     // ---- stage B: phi q_k, BR r_k, phi A^T, BR B^T  (:421-481)
-    for (uint32_t task = t; task < 2 * nn + 2 * n; task += NT) {
-        if (task < nn) sTh[task] = gemm_elem<true>(sPhi, sA, n, n, n, task % n, task / n);
-        else if (task < 2 * nn) { const uint32_t e = task - nn; sBRBt[e] = gemm_elem<true>(sBR, sB, n, m, n, e % n, e / n); }
-        else if (task < 2 * nn + n) { const uint32_t e = task - 2 * nn; sx0[e] = matvec_elem(sPhi, sqk, n, n, e); }
-        else { const uint32_t e = task - 2 * nn - n; sx1[e] = matvec_elem(sBR, srk, n, m, e); }
+    for (uint32_t slot = t; slot < S_SQ + T_SQ + 2 * HN; slot += NT) {
+        if (slot < S_SQ) {
+            if (slot < T_SQ) {
+                const uint32_t r = 2 * (slot % HN), cc = 2 * (slot / HN);
+                float o[4];
+                gemm_2x2<n, n, n, true>(sPhi, sA, r, cc, o);
+                *reinterpret_cast<float2 *>(sTh + cc * n + r) = make_float2(o[0], o[1]);
+                *reinterpret_cast<float2 *>(sTh + (cc + 1) * n + r) = make_float2(o[2], o[3]);
+            }
+        } else if (slot < S_SQ + T_SQ) {
+            const uint32_t e = slot - S_SQ, r = 2 * (e % HN), cc = 2 * (e / HN);
+            float o[4];
+            gemm_2x2<n, m, n, true>(sBR, sB, r, cc, o);
+            *reinterpret_cast<float2 *>(sBRBt + cc * n + r) = make_float2(o[0], o[1]);
+            *reinterpret_cast<float2 *>(sBRBt + (cc + 1) * n + r) = make_float2(o[2], o[3]);
+        } else if (slot < S_SQ + T_SQ + HN) {
+            const uint32_t r = 2 * (slot - S_SQ - T_SQ);
+            float o[2];
+            matvec_2<n, n>(sPhi, sqk, r, o);
+            sx0[r] = o[0];
+            sx0[r + 1] = o[1];
+        } else {
+            const uint32_t r = 2 * (slot - S_SQ - T_SQ - HN);
+            float o[2];
+            matvec_2<n, m>(sBR, srk, r, o);
+            sx1[r] = o[0];
+            sx1[r + 1] = o[1];
+        }
     }
     __syncthreads();
     // ---- stage C: theta = (phi A^T + Q_kp1^-1) + BR B^T ; gamma ; S tiles  (:417, :441-443, :466-500, :527-560)
@@ -256,7 +373,7 @@ schur_phase2_kernel(uint32_t N, float *__restrict__ G, const float *__restrict__
     using namespace schur_detail;
     using K = SchurShape<n, m>;
     constexpr uint32_t nn = K::nn, mm = K::mm, NT = K::NT;
-    extern __shared__ float sm[];
+    extern __shared__ __align__(16) float sm[];
     float *sTk = sm, *sTm = sTk + nn, *sTp = sTm + nn, *sPhik = sTp + nn, *sPhiT = sPhik + nn, *sL = sPhiT + nn, *sRr = sL + nn;
     const uint32_t t = threadIdx.x, b = blockIdx.x;
     {
@@ -281,14 +398,30 @@ schur_phase2_kernel(uint32_t N, float *__restrict__ G, const float *__restrict__
         if (has_r) { sTp[i] = (Prow + 3 * nn)[nn + i]; sPhiT[(i % n) * n + i / n] = S[(size_t)(b + 1) * 3 * nn + i]; }
     }
     __syncthreads();
-    for (uint32_t task = t; task < 2 * nn; task += NT) {
-        if (task < nn) { if (has_l) sL[task] = gemm_elem<false>(sTk, sPhik, n, n, n, task % n, task / n); }
-        else if (has_r) { const uint32_t e = task - nn; sRr[e] = gemm_elem<false>(sTk, sPhiT, n, n, n, e % n, e / n); }
+    // register-blocked 2 x 2 tasks, the left and the right product on warp boundaries (see gemm_2x2)
+    constexpr uint32_t HN = n / 2, T_SQ = HN * HN, S_SQ = (T_SQ + 31) / 32 * 32;
+    for (uint32_t slot = t; slot < S_SQ + T_SQ; slot += NT) {
+        const bool lft = slot < S_SQ;
+        const uint32_t e = lft ? slot : slot - S_SQ, r = 2 * (e % HN), cc = 2 * (e / HN);
+        if (e >= T_SQ || !(lft ? has_l : has_r)) continue;
+        float o[4];
+        gemm_2x2<n, n, n, false>(sTk, lft ? sPhik : sPhiT, r, cc, o);
+        float *dst = lft ? sL : sRr;
+        *reinterpret_cast<float2 *>(dst + cc * n + r) = make_float2(o[0], o[1]);
+        *reinterpret_cast<float2 *>(dst + (cc + 1) * n + r) = make_float2(o[2], o[3]);
     }
     __syncthreads();
-    for (uint32_t task = t; task < 2 * nn; task += NT) {
-        if (task < nn) { if (has_l) Prow[task] = gemm_elem<false>(sL, sTm, n, n, n, task % n, task / n) * -1.0f; }
-        else if (has_r) { const uint32_t e = task - nn; Prow[2 * nn + e] = gemm_elem<false>(sRr, sTp, n, n, n, e % n, e / n) * -1.0f; }
+    for (uint32_t slot = t; slot < S_SQ + T_SQ; slot += NT) {
+        const bool lft = slot < S_SQ;
+        const uint32_t e = lft ? slot : slot - S_SQ, r = 2 * (e % HN), cc = 2 * (e / HN);
+        if (e >= T_SQ || !(lft ? has_l : has_r)) continue;
+        float o[4];
+        gemm_2x2<n, n, n, false>(lft ? sL : sRr, lft ? sTm : sTp, r, cc, o);
+        float *dst = Prow + (lft ? 0u : 2 * nn);
+        dst[cc * n + r] = o[0] * -1.0f;
+        dst[cc * n + r + 1] = o[1] * -1.0f;
+        dst[(cc + 1) * n + r] = o[2] * -1.0f;
+        dst[(cc + 1) * n + r + 1] = o[3] * -1.0f;
     }
 }
 
