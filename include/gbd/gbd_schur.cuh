@@ -122,6 +122,56 @@ __device__ __forceinline__ void gj_warp(float *A, float *snap, uint32_t lane)
 }
 template <uint32_t DIM>
 __device__ __forceinline__ void gj_div_warp(float *A, float *snap, uint32_t lane) { gj_warp<DIM, true>(A, snap, lane); }
+// The several-matrices form on TWO matrices at once by one warp: lanes 0..15 hold the rows of AX, lanes 16..31 the rows of AY,
+// each half with its own pair of snapshots (snap: 64 floats).  Where gj_regs<DIM, true> spends its upper half-warp on the
+// quotients of the new pivot row, here every lane forms two quotients per pivot -- its row factor col[row]/piv and the pivot-row
+// element rowv[lane]/piv -- so a pass over the 14 pivots inverts both matrices.  Same operands and operations per element.
+template <uint32_t DIM>
+__device__ __forceinline__ void gj_div_pair_warp(float *AX, float *AY, float *snap, uint32_t lane)
+{
+    static_assert(DIM + 1 <= 16, "a matrix per half-warp: DIM rows, DIM + 1 pivot-row quotients");
+    const uint32_t half = lane >> 4, hl = lane & 15u;
+    const uint32_t r = hl < DIM ? hl : 0;                // lanes DIM..15 of a half shadow row 0 (never stored)
+    const uint32_t cI = hl <= DIM ? hl : 0;
+    float *A = half ? AY : AX;
+    float *row = snap + 32 * half, *nrow = row + 16;
+    float a[2 * DIM];
+#pragma unroll
+    for (uint32_t c = 0; c < DIM; ++c) {
+        a[c] = A[c * DIM + r];
+        a[DIM + c] = (c == r) ? 1.0f : 0.0f;
+    }
+#pragma unroll
+    for (uint32_t p = 0; p < DIM; ++p) {
+        if (hl == p) {
+#pragma unroll
+            for (uint32_t c = 0; c <= DIM; ++c) row[c] = a[p + c];
+        }
+        __syncwarp();
+        const float piv = row[0];
+        const float q = __fdiv_rn(a[p], piv), nq = __fdiv_rn(row[cI], piv);
+        if (hl <= DIM) nrow[cI] = nq;
+        __syncwarp();
+        constexpr uint32_t NV4 = (DIM + 4) / 4;
+        const float4 *src = reinterpret_cast<const float4 *>(hl == p ? nrow : row);
+#pragma unroll
+        for (uint32_t i = 0; i < NV4; ++i) {
+            const float4 f = src[i];
+            const float v[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+            for (uint32_t e = 0; e < 4; ++e) {
+                const uint32_t c = 4 * i + e;
+                if (c <= DIM) a[p + c] = (hl == p) ? v[e] : fma_(-q, v[e], a[p + c]);
+            }
+        }
+        __syncwarp();
+    }
+    if (hl < DIM) {
+#pragma unroll
+        for (uint32_t c = 0; c < DIM; ++c) A[(DIM + c) * DIM + hl] = a[DIM + c];
+    }
+    __syncwarp();
+}
 template <uint32_t DIM>
 __device__ __forceinline__ void gj_rcp_warp(float *A, float *snap, uint32_t lane) { gj_warp<DIM, false>(A, snap, lane); }
 
@@ -219,27 +269,36 @@ struct SchurShape {
     // phase-1 shared memory (floats)
     static constexpr uint32_t P1_FLOATS = nn /*A*/ + nm /*B*/ + 2 * nn /*Qk|I*/ + 2 * nn /*Qkp1|I*/ + 2 * mm /*R|I*/ + nn /*phi*/ + nm /*BR*/ +
                                           2 * nn /*theta|I*/ + nn /*BRBt*/ + 6 * n + m + 3 + 3 * 32;   // + alignment slack + 3 pivot-row snapshots
+    static constexpr uint32_t P1_STRIDE = (P1_FLOATS + 3) / 4 * 4;     // per warp in the warp-per-row kernel (NT / 32 rows per CTA)
     static constexpr uint32_t P2_FLOATS = 7 * nn;
 };
 
-// ---- phase 1: one CTA per block row (linsys_setup.cuh:139-562)
-template <uint32_t n, uint32_t m>
-__global__ void __launch_bounds__(SchurShape<n, m>::NT, 8)
+// ---- phase 1: one CTA per block row (linsys_setup.cuh:139-562); WR (batches): one WARP per block row, four rows per CTA.
+// With one CTA per row the three inversions run side by side in three warps and the fourth idles, then one warp inverts theta
+// while three idle: right for the latency of one trajectory, but in a batch 42 % of the resident warp-time sat at CTA barriers
+// (ncu, 1024 trajectories).  WR runs the same statements with a warp as the whole team (the inversions one after the other, a
+// __syncwarp where the CTA version has a barrier), so every resident warp always has work.  Same operations per element in both.
+template <uint32_t n, uint32_t m, bool WR = false>
+__global__ void __launch_bounds__(SchurShape<n, m>::NT, WR ? 6 : 8)
 schur_phase1_kernel(uint32_t N, const float *__restrict__ G, const float *__restrict__ C, const float *__restrict__ g,
                     const float *__restrict__ c, float *__restrict__ S, float *__restrict__ Pinv, float *__restrict__ gamma, float rho)
 {
     using namespace schur_detail;
     using K = SchurShape<n, m>;
-    constexpr uint32_t nn = K::nn, mm = K::mm, nm = K::nm, NT = K::NT;
+    constexpr uint32_t nn = K::nn, mm = K::mm, nm = K::nm, NT = WR ? 32u : K::NT;
+    auto team_sync = [] { if constexpr (WR) __syncwarp(); else __syncthreads(); };
     static_assert(n % 2 == 0, "the blocked products pair the rows of column-major n x n operands");
     extern __shared__ __align__(16) float sm[];
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // phase 2 may be scheduled; it waits for our completion
-    float *sA = sm, *sB = sA + nn, *sQk = sB + nm, *sQk_i = sQk + nn, *sQp = sQk_i + nn, *sQp_i = sQp + nn;
+    const uint32_t lane = threadIdx.x & 31u, warp = WR ? 0u : threadIdx.x >> 5, t = WR ? lane : threadIdx.x;
+    const uint32_t b = WR ? blockIdx.x * (K::NT / 32) + (threadIdx.x >> 5) : blockIdx.x;
+    if (WR && b >= N) return;                                    // (a whole warp; WR has no CTA barriers)
+    float *const sm0 = sm + (WR ? (threadIdx.x >> 5) * K::P1_STRIDE : 0u);
+    float *sA = sm0, *sB = sA + nn, *sQk = sB + nm, *sQk_i = sQk + nn, *sQp = sQk_i + nn, *sQp_i = sQp + nn;
     float *sR = sQp_i + nn, *sR_i = sR + mm, *sPhi = sR_i + mm, *sBR = sPhi + nn, *sTh = sBR + nm, *sTh_i = sTh + nn;
     float *sBRBt = sTh_i + nn, *sqk = sBRBt + nn, *sqp = sqk + n, *srk = sqp + n, *sgam = srk + m, *sx0 = sgam + n, *sx1 = sx0 + n;
     float *sc = sx1 + n;
-    float *snap = sm + ((sc + n - sm) + 3) / 4 * 4;              // 3 snapshots of 32 floats, 16-byte aligned
-    const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5, b = blockIdx.x;
+    float *snap = sm0 + ((sc + n - sm0) + 3) / 4 * 4;            // 3 snapshots of 32 floats, 16-byte aligned
     {   // blockIdx.y = system of a batch: every array carries a leading [batch] dimension
         const size_t sys = blockIdx.y;
         G += sys * ((size_t)K::GSET * (N - 1) + nn); C += sys * (size_t)K::CSET * (N - 1); g += sys * ((size_t)(n + m) * (N - 1) + n);
@@ -251,11 +310,11 @@ schur_phase1_kernel(uint32_t N, const float *__restrict__ G, const float *__rest
         // ---- leading block (:151-278): Pinv_00 = -(Q_0 + rho I), S_00 = -Q_0^-1, gamma_0 = -Q_0^-1 q_0
         for (uint32_t i = t; i < nn; i += NT) sQk[i] = (i % n == i / n) ? __fadd_rn(G[i], rho) : G[i];
         for (uint32_t i = t; i < n; i += NT) sqk[i] = g[i];
-        __syncthreads();
+        team_sync();
         for (uint32_t i = t; i < nn; i += NT) Prow[nn + i] = sQk[i] * -1.0f;
-        __syncthreads();
+        team_sync();
         if (warp == 0) gj_div_warp<n>(sQk, snap, lane);
-        __syncthreads();
+        team_sync();
         for (uint32_t i = t; i < nn; i += NT) Srow[nn + i] = sQk_i[i] * -1.0f;
         for (uint32_t i = t; i < n; i += NT) gamma[i] = -matvec_elem(sQk_i, sqk, n, n, i);
         return;
@@ -276,12 +335,17 @@ schur_phase1_kernel(uint32_t N, const float *__restrict__ G, const float *__rest
         sc[i] = c[(size_t)b * n + i];
     }
     for (uint32_t i = t; i < m; i += NT) srk[i] = g[(size_t)(b - 1) * (n + m) + n + i];
-    __syncthreads();
+    team_sync();
     // ---- the three inversions side by side, one warp each (:351-363)
-    if (warp == 0) gj_div_warp<n>(sQk, snap, lane);
-    else if (warp == 1) gj_div_warp<n>(sQp, snap + 32, lane);
-    else if (warp == 2) gj_div_warp<m>(sR, snap + 64, lane);
-    __syncthreads();
+    if constexpr (WR) {
+        gj_div_pair_warp<n>(sQk, sQp, snap, lane);       // both state-cost blocks in one pass, a half-warp each
+        gj_div_warp<m>(sR, snap + 64, lane);
+    } else {
+        if (warp == 0) gj_div_warp<n>(sQk, snap, lane);
+        else if (warp == 1) gj_div_warp<n>(sQp, snap + 32, lane);
+        else if (warp == 2) gj_div_warp<m>(sR, snap + 64, lane);
+    }
+    team_sync();
     // park the inverses for compute_dz in tiles that phase 2 overwrites (moved into G there): Q_{b-1}^-1 in the left
     // tile of row b, R_{b-1}^-1 in the right tile of row b-1, Q_{N-1}^-1 in the pad tile (left of row 0)
     for (uint32_t i = t; i < nn; i += NT) Prow[i] = sQk_i[i];
@@ -313,7 +377,7 @@ schur_phase1_kernel(uint32_t N, const float *__restrict__ G, const float *__rest
             sgam[r + 1] = o[1];
         }
     }
-    __syncthreads();
+    team_sync();
     // ---- stage B: phi q_k, BR r_k, phi A^T, BR B^T  (:421-481)
     for (uint32_t slot = t; slot < S_SQ + T_SQ + 2 * HN; slot += NT) {
         if (slot < S_SQ) {
@@ -344,7 +408,7 @@ schur_phase1_kernel(uint32_t N, const float *__restrict__ G, const float *__rest
             sx1[r + 1] = o[1];
         }
     }
-    __syncthreads();
+    team_sync();
     // ---- stage C: theta = (phi A^T + Q_kp1^-1) + BR B^T ; gamma ; S tiles  (:417, :441-443, :466-500, :527-560)
     for (uint32_t i = t; i < nn; i += NT) {
         const float th = __fadd_rn(__fadd_rn(sTh[i], sQp_i[i]), sBRBt[i]);
@@ -357,10 +421,10 @@ schur_phase1_kernel(uint32_t N, const float *__restrict__ G, const float *__rest
         const float gm = __fadd_rn(__fadd_rn(sgam[i], -sc[i]), __fadd_rn(sx1[i], sx0[i]));
         gamma[(size_t)b * n + i] = gm * -1.0f;
     }
-    __syncthreads();
+    team_sync();
     // ---- theta^-1 (:503-518)
     if (warp == 0) gj_rcp_warp<n>(sTh, snap, lane);
-    __syncthreads();
+    team_sync();
     for (uint32_t i = t; i < nn; i += NT) Prow[nn + i] = sTh_i[i] * -1.0f;
 }
 

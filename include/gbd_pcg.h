@@ -171,6 +171,10 @@ int gbd_pcg_plan_solve_host_f64(gbd_pcg_plan *plan, const double *h_S, const dou
  * (gbd_schur_supported); GBD_PCG_ERR_UNSUPPORTED otherwise.
  */
 int gbd_schur_supported(uint32_t n, uint32_t m);
+/* How the assembly's first phase is mapped: 0 = one CTA per block row (lowest latency: the launch for one trajectory), 1 = one
+ * warp per block row (highest throughput: no CTA barriers, the launch for batches), -1 (default) = by size: warp-per-row when
+ * batch * N >= 4096 block rows.  Both run the same operations per element (bit-identical results).  Returns the previous mode. */
+int gbd_schur_set_team(int mode);
 int gbd_form_schur_system_f32(uint32_t n, uint32_t m, uint32_t N, float *d_G, const float *d_C, const float *d_g,
                               const float *d_c, float *d_S, float *d_Pinv, float *d_gamma, float rho, void *stream);
 int gbd_compute_dz_f32(uint32_t n, uint32_t m, uint32_t N, const float *d_Ginv, const float *d_C, const float *d_g,

@@ -23,7 +23,7 @@ SYMBOLS = [
     "gbd_step_device_flags", "gbd_schur_csr_nnz", "gbd_schur_csr_pattern_i32", "gbd_schur_csr_values_f32",
     "gbd_bcr_supported", "gbd_bcr_solve_f32", "gbd_bcr_solve_batched_f32", "gbd_bcr_solve_flagged_f32",
     "gbd_step_run_fallback_f32", "gbd_pcg_set_numerics", "gbd_pcg_get_numerics", "gbd_pcg_resolved_variant",
-    "gbd_pcg_plan_invalidate",
+    "gbd_pcg_plan_invalidate", "gbd_schur_set_team",
 ]
 
 _lib = None
@@ -77,6 +77,8 @@ def lib():
     L.gbd_pcg_plan_solve_host_f64.restype = C.c_int
     L.gbd_pcg_plan_solve_host_f64.argtypes = [vp, vp, vp, vp, vp, u32, f64, vp, vp]
     L.gbd_pcg_launch_count.restype = C.c_uint64
+    L.gbd_schur_set_team.restype = C.c_int
+    L.gbd_schur_set_team.argtypes = [C.c_int]
     L.gbd_schur_supported.restype = C.c_int
     L.gbd_schur_supported.argtypes = [u32, u32]
     L.gbd_form_schur_system_f32.restype = C.c_int

@@ -631,13 +631,21 @@ int gbd_pcg_plan_solve_host_f64(gbd_pcg_plan *plan, const double *h_S, const dou
 }  // extern "C"
 
 namespace {
+std::atomic<int> g_schur_team{-1};          // gbd_schur_set_team
 template <uint32_t n, uint32_t m>
 int schur_launch(uint32_t N, uint32_t batch, float *G, const float *C, const float *g, const float *c, float *S, float *P, float *gam,
                  float rho, cudaStream_t st)
 {
     using K = gbd::SchurShape<n, m>;
     { const int drc = check_device(); if (drc) return drc; }
-    gbd::schur_phase1_kernel<n, m><<<dim3(N, batch), K::NT, K::P1_FLOATS * sizeof(float), st>>>(N, G, C, g, c, S, P, gam, rho);
+    const int team = g_schur_team.load(std::memory_order_relaxed);
+    if (team == 1 || (team < 0 && (uint64_t)batch * N >= 4096u)) {       // batches: one warp per block row, four rows per CTA
+        constexpr uint32_t RPC = K::NT / 32;
+        gbd::schur_phase1_kernel<n, m, true><<<dim3((N + RPC - 1) / RPC, batch), K::NT, RPC * K::P1_STRIDE * sizeof(float), st>>>(
+            N, G, C, g, c, S, P, gam, rho);
+    } else {
+        gbd::schur_phase1_kernel<n, m, false><<<dim3(N, batch), K::NT, K::P1_FLOATS * sizeof(float), st>>>(N, G, C, g, c, S, P, gam, rho);
+    }
     {   // phase 2 with programmatic stream serialization: its launch overlaps phase 1, griddepcontrol.wait orders the data
         cudaLaunchConfig_t cfg = {};
         cudaLaunchAttribute at[1];
@@ -680,6 +688,8 @@ int gbd_schur_supported(uint32_t n, uint32_t m)
 #undef X
     return 0;
 }
+
+int gbd_schur_set_team(int mode) { return g_schur_team.exchange(mode < 0 ? -1 : (mode ? 1 : 0)); }
 
 int gbd_form_schur_system_f32(uint32_t n, uint32_t m, uint32_t N, float *d_G, const float *d_C, const float *d_g,
                               const float *d_c, float *d_S, float *d_Pinv, float *d_gamma, float rho, void *stream)

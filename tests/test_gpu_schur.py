@@ -27,6 +27,15 @@ def _mask_pads(x, n, N):
     return x
 
 
+@pytest.fixture(params=[0, 1], ids=["cta_per_row", "warp_per_row"])
+def team(request):
+    """Both mappings of the assembly's first phase (gbd_schur_set_team): the latency launch and the batch launch."""
+    from mpcgpu_b200 import _capi
+    prev = _capi.lib().gbd_schur_set_team(request.param)
+    yield request.param
+    _capi.lib().gbd_schur_set_team(prev)
+
+
 def _ours(torch, n, m, N, G, C, g, c, rho):
     import mpcgpu_b200 as mp
     dG, dC, dg, dc = (torch.from_numpy(x.copy()).cuda() for x in (G, C, g, c))
@@ -39,7 +48,7 @@ def _ours(torch, n, m, N, G, C, g, c, rho):
 
 
 @pytest.mark.parametrize("n,m,N", [(14, 7, 8), (14, 7, 32), (14, 7, 128), (14, 7, 512), (6, 3, 12), (4, 2, 5), (2, 1, 3)])
-def test_form_schur_bit_exact_vs_oracle(torch_cuda, n, m, N):
+def test_form_schur_bit_exact_vs_oracle(torch_cuda, team, n, m, N):
     from oracle import schur
     G, C, g, c = schur.make_kkt(n, m, N, seed=100 + n + N)
     want = schur.form(G, C, g, c, n, m, N, 1e-3)
@@ -51,7 +60,7 @@ def test_form_schur_bit_exact_vs_oracle(torch_cuda, n, m, N):
 
 
 @pytest.mark.parametrize("n,m,N", [(14, 7, 32), (14, 7, 128), (6, 3, 12)])
-def test_form_schur_and_dz_bit_exact_vs_reference_kernels(torch_cuda, n, m, N):
+def test_form_schur_and_dz_bit_exact_vs_reference_kernels(torch_cuda, team, n, m, N):
     """A/B against the reference's own form_schur_system / compute_dz compiled for sm_100a (oracle/_ref/libref_schur.so)."""
     torch = torch_cuda
     from oracle import refgpu, schur
@@ -142,7 +151,7 @@ def test_form_schur_and_dz_on_reference_minted_iiwa_vectors(torch_cuda):
 
 
 @pytest.mark.parametrize("n,m,N,B", [(14, 7, 32, 5), (14, 7, 128, 3)])
-def test_batched_step_plan_equals_per_system_oracle_chain(torch_cuda, n, m, N, B):
+def test_batched_step_plan_equals_per_system_oracle_chain(torch_cuda, team, n, m, N, B):
     """gbd_step_run_f32 (row f3): assembly -> warm-started solve -> dz for a batch, one enqueue; every trajectory equals the
     oracle chain bit for bit, and the flags the multi-GPU driver gathers are the per-trajectory max_iter_exit."""
     torch = torch_cuda
