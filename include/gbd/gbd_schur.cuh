@@ -267,8 +267,10 @@ struct SchurShape {
     static constexpr uint32_t nn = n * n, mm = m * m, nm = n * m;
     static constexpr uint32_t GSET = nn + mm, CSET = nn + nm;
     // phase-1 shared memory (floats)
-    static constexpr uint32_t P1_FLOATS = nn /*A*/ + nm /*B*/ + 2 * nn /*Qk|I*/ + 2 * nn /*Qkp1|I*/ + 2 * mm /*R|I*/ + nn /*phi*/ + nm /*BR*/ +
-                                          2 * nn /*theta|I*/ + nn /*BRBt*/ + 6 * n + m + 3 + 3 * 32;   // + alignment slack + 3 pivot-row snapshots
+    // phi, BR and theta|theta^-1 live in the buffers of Q_k, Q_kp1 and Q_k^-1|Q_kp1, which are dead by the time they are written
+    // (6.2 KB per block row instead of 9 KB at n = 14: eight rows' worth more resident per SM in the warp-per-row launch)
+    static constexpr uint32_t P1_FLOATS = nn /*A*/ + nm /*B*/ + 2 * nn /*Qk|I*/ + 2 * nn /*Qkp1|I*/ + 2 * mm /*R|I*/ + nn /*BRBt*/ +
+                                          6 * n + m + 3 + 3 * 32;                                      // + alignment slack + 3 pivot-row snapshots
     static constexpr uint32_t P1_STRIDE = (P1_FLOATS + 3) / 4 * 4;     // per warp in the warp-per-row kernel (NT / 32 rows per CTA)
     static constexpr uint32_t P2_FLOATS = 7 * nn;
 };
@@ -279,7 +281,7 @@ struct SchurShape {
 // (ncu, 1024 trajectories).  WR runs the same statements with a warp as the whole team (the inversions one after the other, a
 // __syncwarp where the CTA version has a barrier), so every resident warp always has work.  Same operations per element in both.
 template <uint32_t n, uint32_t m, bool WR = false>
-__global__ void __launch_bounds__(SchurShape<n, m>::NT, WR ? 6 : 8)
+__global__ void __launch_bounds__(SchurShape<n, m>::NT, 8)
 schur_phase1_kernel(uint32_t N, const float *__restrict__ G, const float *__restrict__ C, const float *__restrict__ g,
                     const float *__restrict__ c, float *__restrict__ S, float *__restrict__ Pinv, float *__restrict__ gamma, float rho)
 {
@@ -295,8 +297,13 @@ schur_phase1_kernel(uint32_t N, const float *__restrict__ G, const float *__rest
     if (WR && b >= N) return;                                    // (a whole warp; WR has no CTA barriers)
     float *const sm0 = sm + (WR ? (threadIdx.x >> 5) * K::P1_STRIDE : 0u);
     float *sA = sm0, *sB = sA + nn, *sQk = sB + nm, *sQk_i = sQk + nn, *sQp = sQk_i + nn, *sQp_i = sQp + nn;
-    float *sR = sQp_i + nn, *sR_i = sR + mm, *sPhi = sR_i + mm, *sBR = sPhi + nn, *sTh = sBR + nm, *sTh_i = sTh + nn;
-    float *sBRBt = sTh_i + nn, *sqk = sBRBt + nn, *sqp = sqk + n, *srk = sqp + n, *sgam = srk + m, *sx0 = sgam + n, *sx1 = sx0 + n;
+    float *sR = sQp_i + nn, *sR_i = sR + mm, *sBRBt = sR_i + mm;
+    // aliases (each is written only after the last read of its host, with a team_sync in between): phi over Q_k (read by its
+    // inversion only), BR over Q_kp1 (same), theta over Q_k^-1 (last read in stage A, parked for dz before that), and theta^-1
+    // behind it over BR (last read in stage B)
+    float *sPhi = sQk, *sBR = sQp, *sTh = sQk_i, *sTh_i = sTh + nn;
+    static_assert(nm <= nn, "BR fits the Q_kp1 buffer");
+    float *sqk = sBRBt + nn, *sqp = sqk + n, *srk = sqp + n, *sgam = srk + m, *sx0 = sgam + n, *sx1 = sx0 + n;
     float *sc = sx1 + n;
     float *snap = sm0 + ((sc + n - sm0) + 3) / 4 * 4;            // 3 snapshots of 32 floats, 16-byte aligned
     {   // blockIdx.y = system of a batch: every array carries a leading [batch] dimension
