@@ -103,77 +103,105 @@ __device__ __forceinline__ void gj_regs(float (&a)[2 * DIM], float *snap, uint32
         __syncwarp();
     }
 }
-template <uint32_t DIM, bool DIV>
-__device__ __forceinline__ void gj_warp(float *A, float *snap, uint32_t lane)
+// ---- the inversions of the assembly kernels: the same updates as gj_regs, held as a SLIDING WINDOW.  At pivot p the reference
+// touches columns p .. p+DIM of [V | I]; column p is a unit vector afterwards and is never read again, and column p+DIM enters
+// the range as the untouched identity column e_p.  So a lane keeps w[c] = column p + c of its row, c = 0 .. DIM: the update of
+// column p + c lands in w[c - 1], the entering identity element in w[DIM], and every register index is the same at every pivot --
+// the pivot loop is a real loop (one copy of ~70 instructions instead of 14: the unrolled form streamed ~70 KB of straight-line
+// code through the instruction cache once per block row, 22 % of the batched kernel's stall cycles) on DIM + 1 registers
+// instead of 2 DIM.  Operands and operations per element are unchanged -> same bits.
+// TEAM lanes form a team around one matrix: 32 (lanes 0..15 rows and row factors, lanes 16..31 the quotients of the new pivot
+// row) or 16 (two matrices per warp, a half-warp each; every lane forms both kinds of quotient).
+// A: V (DIM x DIM, column-major) followed by DIM x DIM floats that receive V^-1;  snap: 32 floats per team, 16-byte aligned.
+template <uint32_t DIM, uint32_t TEAM>
+__device__ __forceinline__ void gj_div_window(float *A, float *snap, uint32_t lane)
 {
-    const uint32_t r = lane < DIM ? lane : 0;            // lanes DIM..15 and 16.. shadow row 0 (never stored)
-    float a[2 * DIM];
-#pragma unroll
-    for (uint32_t c = 0; c < DIM; ++c) {
-        a[c] = A[c * DIM + r];
-        a[DIM + c] = (c == r) ? 1.0f : 0.0f;
-    }
-    gj_regs<DIM, DIV>(a, snap, lane);
-    if (lane < DIM) {
-#pragma unroll
-        for (uint32_t c = 0; c < DIM; ++c) A[(DIM + c) * DIM + lane] = a[DIM + c];
-    }
-    __syncwarp();
-}
-template <uint32_t DIM>
-__device__ __forceinline__ void gj_div_warp(float *A, float *snap, uint32_t lane) { gj_warp<DIM, true>(A, snap, lane); }
-// The several-matrices form on TWO matrices at once by one warp: lanes 0..15 hold the rows of AX, lanes 16..31 the rows of AY,
-// each half with its own pair of snapshots (snap: 64 floats).  Where gj_regs<DIM, true> spends its upper half-warp on the
-// quotients of the new pivot row, here every lane forms two quotients per pivot -- its row factor col[row]/piv and the pivot-row
-// element rowv[lane]/piv -- so a pass over the 14 pivots inverts both matrices.  Same operands and operations per element.
-template <uint32_t DIM>
-__device__ __forceinline__ void gj_div_pair_warp(float *AX, float *AY, float *snap, uint32_t lane)
-{
-    static_assert(DIM + 1 <= 16, "a matrix per half-warp: DIM rows, DIM + 1 pivot-row quotients");
-    const uint32_t half = lane >> 4, hl = lane & 15u;
-    const uint32_t r = hl < DIM ? hl : 0;                // lanes DIM..15 of a half shadow row 0 (never stored)
+    static_assert(DIM + 1 <= 16 && (TEAM == 16 || TEAM == 32), "DIM rows and DIM + 1 pivot-row quotients per 16 lanes");
+    const uint32_t hl = lane & 15u, upper = (lane >> 4) & 1u;
+    const uint32_t r = hl < DIM ? hl : 0;                        // lanes DIM..15 shadow row 0 (never stored)
     const uint32_t cI = hl <= DIM ? hl : 0;
-    float *A = half ? AY : AX;
-    float *row = snap + 32 * half, *nrow = row + 16;
-    float a[2 * DIM];
+    const bool rows = TEAM == 16 || !upper;                      // this lane holds a matrix row ...
+    const bool quot = TEAM == 16 || upper;                       // ... and/or forms pivot-row quotients
+    float *row = snap + (TEAM == 16 ? 32 * upper : 0u), *nrow = row + 16;
+    const uint32_t me = rows ? hl : 32u;                         // my row index as a pivot (never matches on a quotient-only lane)
+    float w[DIM + 1];
 #pragma unroll
-    for (uint32_t c = 0; c < DIM; ++c) {
-        a[c] = A[c * DIM + r];
-        a[DIM + c] = (c == r) ? 1.0f : 0.0f;
-    }
-#pragma unroll
+    for (uint32_t c = 0; c < DIM; ++c) w[c] = A[c * DIM + r];
+    w[DIM] = r == 0 ? 1.0f : 0.0f;
+#pragma unroll 1
     for (uint32_t p = 0; p < DIM; ++p) {
-        if (hl == p) {
+        if (me == p) {
 #pragma unroll
-            for (uint32_t c = 0; c <= DIM; ++c) row[c] = a[p + c];
+            for (uint32_t c = 0; c <= DIM; ++c) row[c] = w[c];
         }
         __syncwarp();
         const float piv = row[0];
-        const float q = __fdiv_rn(a[p], piv), nq = __fdiv_rn(row[cI], piv);
-        if (hl <= DIM) nrow[cI] = nq;
+        float q, nq;
+        if constexpr (TEAM == 16) {
+            q = __fdiv_rn(w[0], piv);
+            nq = __fdiv_rn(row[cI], piv);
+        } else {
+            q = nq = __fdiv_rn(upper ? row[cI] : w[0], piv);     // one division sequence serves both kinds of quotient
+        }
+        if (quot && hl <= DIM) nrow[cI] = nq;
         __syncwarp();
+        // lane p takes the new pivot row, every other lane the old one: one address select, then 128-bit loads
         constexpr uint32_t NV4 = (DIM + 4) / 4;
-        const float4 *src = reinterpret_cast<const float4 *>(hl == p ? nrow : row);
+        const float4 *src = reinterpret_cast<const float4 *>(me == p ? nrow : row);
+        float v[4 * NV4];
 #pragma unroll
         for (uint32_t i = 0; i < NV4; ++i) {
             const float4 f = src[i];
-            const float v[4] = {f.x, f.y, f.z, f.w};
-#pragma unroll
-            for (uint32_t e = 0; e < 4; ++e) {
-                const uint32_t c = 4 * i + e;
-                if (c <= DIM) a[p + c] = (hl == p) ? v[e] : fma_(-q, v[e], a[p + c]);
-            }
+            v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
         }
+#pragma unroll
+        for (uint32_t c = 1; c <= DIM; ++c) w[c - 1] = (me == p) ? v[c] : fma_(-q, v[c], w[c]);
+        w[DIM] = r == p + 1 ? 1.0f : 0.0f;
         __syncwarp();
     }
-    if (hl < DIM) {
+    if (rows && hl < DIM) {
 #pragma unroll
-        for (uint32_t c = 0; c < DIM; ++c) A[(DIM + c) * DIM + hl] = a[DIM + c];
+        for (uint32_t c = 0; c < DIM; ++c) A[(DIM + c) * DIM + hl] = w[c];
     }
     __syncwarp();
 }
 template <uint32_t DIM>
-__device__ __forceinline__ void gj_rcp_warp(float *A, float *snap, uint32_t lane) { gj_warp<DIM, false>(A, snap, lane); }
+__device__ __forceinline__ void gj_div_warp(float *A, float *snap, uint32_t lane) { gj_div_window<DIM, 32>(A, snap, lane); }
+// the several-matrices form on TWO matrices at once by one warp: lanes 0..15 on AX, lanes 16..31 on AY (snap: 64 floats)
+template <uint32_t DIM>
+__device__ __forceinline__ void gj_div_pair_warp(float *AX, float *AY, float *snap, uint32_t lane)
+{
+    gj_div_window<DIM, 16>(lane & 16u ? AY : AX, snap, lane);
+}
+// single-matrix form (matrix.cuh:120-146): pvInv = 1 / piv; row == p : x * pvInv, else fma(-(col[row] * pvInv), rowv[c], x).
+// No lane needs another lane's quotient, so the pivot row travels by shuffles.
+template <uint32_t DIM>
+__device__ __forceinline__ void gj_rcp_warp(float *A, float *snap, uint32_t lane)
+{
+    (void)snap;
+    const uint32_t r = lane < DIM ? lane : 0;
+    float w[DIM + 1];
+#pragma unroll
+    for (uint32_t c = 0; c < DIM; ++c) w[c] = A[c * DIM + r];
+    w[DIM] = r == 0 ? 1.0f : 0.0f;
+#pragma unroll 1
+    for (uint32_t p = 0; p < DIM; ++p) {
+        const float piv = __shfl_sync(0xffffffffu, w[0], p);
+        const float pv_inv = __fdiv_rn(1.0f, piv);
+        const float f = __fmul_rn(w[0], pv_inv);
+#pragma unroll
+        for (uint32_t c = 1; c <= DIM; ++c) {
+            const float rv = __shfl_sync(0xffffffffu, w[c], p);
+            w[c - 1] = (lane == p) ? __fmul_rn(rv, pv_inv) : fma_(-f, rv, w[c]);
+        }
+        w[DIM] = r == p + 1 ? 1.0f : 0.0f;
+    }
+    if (lane < DIM) {
+#pragma unroll
+        for (uint32_t c = 0; c < DIM; ++c) A[(DIM + c) * DIM + lane] = w[c];
+    }
+    __syncwarp();
+}
 
 // one element of C (M x NC) = A (M x K) * B (K x NC)  [TB: A * B^T with B stored NC x K], column-major,
 // one FMA per term in ascending k (GLASS/src/L3/gemm.cuh:47-96)
