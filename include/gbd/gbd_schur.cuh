@@ -113,8 +113,10 @@ __device__ __forceinline__ void gj_regs(float (&a)[2 * DIM], float *snap, uint32
 // TEAM lanes form a team around one matrix: 32 (lanes 0..15 rows and row factors, lanes 16..31 the quotients of the new pivot
 // row) or 16 (two matrices per warp, a half-warp each; every lane forms both kinds of quotient).
 // A: V (DIM x DIM, column-major) followed by DIM x DIM floats that receive V^-1;  snap: 32 floats per team, 16-byte aligned.
+// Gsrc != nullptr: V is read straight from global memory with rho added on the diagonal (the reference's Q + rho I), so the
+// block never passes through shared memory on its way into the registers; only V^-1 is written to A + DIM * DIM.
 template <uint32_t DIM, uint32_t TEAM>
-__device__ __forceinline__ void gj_div_window(float *A, float *snap, uint32_t lane)
+__device__ __forceinline__ void gj_div_window(float *A, float *snap, uint32_t lane, const float *Gsrc = nullptr, float rho = 0.0f)
 {
     static_assert(DIM + 1 <= 16 && (TEAM == 16 || TEAM == 32), "DIM rows and DIM + 1 pivot-row quotients per 16 lanes");
     const uint32_t hl = lane & 15u, upper = (lane >> 4) & 1u;
@@ -125,8 +127,15 @@ __device__ __forceinline__ void gj_div_window(float *A, float *snap, uint32_t la
     float *row = snap + (TEAM == 16 ? 32 * upper : 0u), *nrow = row + 16;
     const uint32_t me = rows ? hl : 32u;                         // my row index as a pivot (never matches on a quotient-only lane)
     float w[DIM + 1];
+    if (Gsrc) {
 #pragma unroll
-    for (uint32_t c = 0; c < DIM; ++c) w[c] = A[c * DIM + r];
+        for (uint32_t c = 0; c < DIM; ++c) w[c] = Gsrc[c * DIM + r];
+#pragma unroll
+        for (uint32_t c = 0; c < DIM; ++c) w[c] = c == r ? __fadd_rn(w[c], rho) : w[c];
+    } else {
+#pragma unroll
+        for (uint32_t c = 0; c < DIM; ++c) w[c] = A[c * DIM + r];
+    }
     w[DIM] = r == 0 ? 1.0f : 0.0f;
 #pragma unroll 1
     for (uint32_t p = 0; p < DIM; ++p) {
@@ -166,12 +175,15 @@ __device__ __forceinline__ void gj_div_window(float *A, float *snap, uint32_t la
     __syncwarp();
 }
 template <uint32_t DIM>
-__device__ __forceinline__ void gj_div_warp(float *A, float *snap, uint32_t lane) { gj_div_window<DIM, 32>(A, snap, lane); }
+__device__ __forceinline__ void gj_div_warp(float *A, float *snap, uint32_t lane, const float *Gsrc = nullptr, float rho = 0.0f)
+{
+    gj_div_window<DIM, 32>(A, snap, lane, Gsrc, rho);
+}
 // the several-matrices form on TWO matrices at once by one warp: lanes 0..15 on AX, lanes 16..31 on AY (snap: 64 floats)
 template <uint32_t DIM>
-__device__ __forceinline__ void gj_div_pair_warp(float *AX, float *AY, float *snap, uint32_t lane)
+__device__ __forceinline__ void gj_div_pair_warp(float *AX, float *AY, float *snap, uint32_t lane, const float *GX, const float *GY, float rho)
 {
-    gj_div_window<DIM, 16>(lane & 16u ? AY : AX, snap, lane);
+    gj_div_window<DIM, 16>(lane & 16u ? AY : AX, snap, lane, lane & 16u ? GY : GX, rho);
 }
 // single-matrix form (matrix.cuh:120-146): pvInv = 1 / piv; row == p : x * pvInv, else fma(-(col[row] * pvInv), rowv[c], x).
 // No lane needs another lane's quotient, so the pivot row travels by shuffles.
@@ -356,14 +368,9 @@ schur_phase1_kernel(uint32_t N, const float *__restrict__ G, const float *__rest
     }
     // ---- block rows 1 .. N-1 (:280-560); the reference's "k" blocks are knot b-1, its "kp1" blocks knot b
     const float *Gk = G + (size_t)(b - 1) * K::GSET, *Gp = G + (size_t)b * K::GSET, *Ck = C + (size_t)(b - 1) * K::CSET;
-    for (uint32_t i = t; i < nn; i += NT) {
-        const bool diag = i % n == i / n;
-        sA[i] = Ck[i];
-        sQk[i] = diag ? __fadd_rn(Gk[i], rho) : Gk[i];
-        sQp[i] = diag ? __fadd_rn(Gp[i], rho) : Gp[i];
-    }
+    // (Q_k, Q_kp1 and R_k go from global memory straight into the registers of their inversions)
+    for (uint32_t i = t; i < nn; i += NT) sA[i] = Ck[i];
     for (uint32_t i = t; i < nm; i += NT) sB[i] = Ck[nn + i];
-    for (uint32_t i = t; i < mm; i += NT) sR[i] = (i % m == i / m) ? __fadd_rn(Gk[nn + i], rho) : Gk[nn + i];
     for (uint32_t i = t; i < n; i += NT) {
         sqk[i] = g[(size_t)(b - 1) * (n + m) + i];
         sqp[i] = g[(size_t)b * (n + m) + i];
@@ -373,12 +380,12 @@ schur_phase1_kernel(uint32_t N, const float *__restrict__ G, const float *__rest
     team_sync();
     // ---- the three inversions side by side, one warp each (:351-363)
     if constexpr (WR) {
-        gj_div_pair_warp<n>(sQk, sQp, snap, lane);       // both state-cost blocks in one pass, a half-warp each
-        gj_div_warp<m>(sR, snap + 64, lane);
+        gj_div_pair_warp<n>(sQk, sQp, snap, lane, Gk, Gp, rho);       // both state-cost blocks in one pass, a half-warp each
+        gj_div_warp<m>(sR, snap + 64, lane, Gk + nn, rho);
     } else {
-        if (warp == 0) gj_div_warp<n>(sQk, snap, lane);
-        else if (warp == 1) gj_div_warp<n>(sQp, snap + 32, lane);
-        else if (warp == 2) gj_div_warp<m>(sR, snap + 64, lane);
+        if (warp == 0) gj_div_warp<n>(sQk, snap, lane, Gk, rho);
+        else if (warp == 1) gj_div_warp<n>(sQp, snap + 32, lane, Gp, rho);
+        else if (warp == 2) gj_div_warp<m>(sR, snap + 64, lane, Gk + nn, rho);
     }
     team_sync();
     // park the inverses for compute_dz in tiles that phase 2 overwrites (moved into G there): Q_{b-1}^-1 in the left
