@@ -19,6 +19,12 @@
 //   every 14-pivot inversion is a CTA barrier pair  run concurrently in three warps on __syncwarp; independent
 //                                                   products (A Q^-1, B R^-1, Q^-1 q ...) share a stage
 //   per-element division in the pivot update        one division per row and pivot (same operands -> same bits)
+//   one mapping                                     two mappings of the same statements: a CTA per block row (one
+//                                                   trajectory: lowest latency) and a WARP per block row with both Q
+//                                                   blocks inverted in one pass (batches: no CTA barrier, every resident
+//                                                   warp always has work)
+//   matrices updated in shared memory               Gauss-Jordan on a sliding register window (n+1 registers per row,
+//                                                   the pivot loop a real loop), products register-blocked 2 x 2
 //   CTA k overwrites G slot k-1 with the inverse    inverses are parked in Pinv tiles that phase 2 overwrites
 //   while CTA k-1 may still read it (a race that    anyway (left tile of row k, right tile of row k-1, the pad
 //   only co-residency hides)                        tile of row 0) and moved into G by the phase-2 CTA that owns
