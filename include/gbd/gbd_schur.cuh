@@ -319,6 +319,8 @@ struct SchurShape {
                                           6 * n + m + 3 + 3 * 32;                                      // + alignment slack + 3 pivot-row snapshots
     static constexpr uint32_t P1_STRIDE = (P1_FLOATS + 3) / 4 * 4;     // per warp in the warp-per-row kernel (NT / 32 rows per CTA)
     static constexpr uint32_t P2_FLOATS = 7 * nn;
+    static constexpr uint32_t P2W_TILE = 16 * 20;                      // warp-per-row phase 2: tiles staged as 16 columns with ld 20
+    static constexpr uint32_t P2W_FLOATS = (NT / 32) * 7 * P2W_TILE;
 };
 
 // ---- phase 1: one CTA per block row (linsys_setup.cuh:139-562); WR (batches): one WARP per block row, four rows per CTA.
@@ -375,15 +377,19 @@ schur_phase1_kernel(uint32_t N, const float *__restrict__ G, const float *__rest
     // ---- block rows 1 .. N-1 (:280-560); the reference's "k" blocks are knot b-1, its "kp1" blocks knot b
     const float *Gk = G + (size_t)(b - 1) * K::GSET, *Gp = G + (size_t)b * K::GSET, *Ck = C + (size_t)(b - 1) * K::CSET;
     // (Q_k, Q_kp1 and R_k go from global memory straight into the registers of their inversions)
-    for (uint32_t i = t; i < nn; i += NT) sA[i] = Ck[i];
-    for (uint32_t i = t; i < nm; i += NT) sB[i] = Ck[nn + i];
+    // A, B and the vectors are first read in stage A: they travel global -> shared memory as 4-byte cp.async copies issued here
+    // and awaited after the inversions, so their DRAM latency hides behind the pivot loops (the inversions read no staged data)
+    auto cp4 = [](float *dst, const float *src) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+    };
+    for (uint32_t i = t; i < nn; i += NT) cp4(sA + i, Ck + i);
+    for (uint32_t i = t; i < nm; i += NT) cp4(sB + i, Ck + nn + i);
     for (uint32_t i = t; i < n; i += NT) {
-        sqk[i] = g[(size_t)(b - 1) * (n + m) + i];
-        sqp[i] = g[(size_t)b * (n + m) + i];
-        sc[i] = c[(size_t)b * n + i];
+        cp4(sqk + i, g + (size_t)(b - 1) * (n + m) + i);
+        cp4(sqp + i, g + (size_t)b * (n + m) + i);
+        cp4(sc + i, c + (size_t)b * n + i);
     }
-    for (uint32_t i = t; i < m; i += NT) srk[i] = g[(size_t)(b - 1) * (n + m) + n + i];
-    team_sync();
+    for (uint32_t i = t; i < m; i += NT) cp4(srk + i, g + (size_t)(b - 1) * (n + m) + n + i);
     // ---- the three inversions side by side, one warp each (:351-363)
     if constexpr (WR) {
         gj_div_pair_warp<n>(sQk, sQp, snap, lane, Gk, Gp, rho);       // both state-cost blocks in one pass, a half-warp each
@@ -393,6 +399,7 @@ schur_phase1_kernel(uint32_t N, const float *__restrict__ G, const float *__rest
         else if (warp == 1) gj_div_warp<n>(sQp, snap + 32, lane, Gp, rho);
         else if (warp == 2) gj_div_warp<m>(sR, snap + 64, lane, Gk + nn, rho);
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
     team_sync();
     // park the inverses for compute_dz in tiles that phase 2 overwrites (moved into G there): Q_{b-1}^-1 in the left
     // tile of row b, R_{b-1}^-1 in the right tile of row b-1, Q_{N-1}^-1 in the pad tile (left of row 0)
@@ -534,6 +541,138 @@ schur_phase2_kernel(uint32_t N, float *__restrict__ G, const float *__restrict__
         dst[cc * n + r + 1] = o[1] * -1.0f;
         dst[(cc + 1) * n + r] = o[2] * -1.0f;
         dst[(cc + 1) * n + r + 1] = o[3] * -1.0f;
+    }
+}
+
+// ---- phase 2 for batches: one WARP per block row, four rows per CTA, no CTA barrier.  ncu on the CTA mapping at 1024
+// trajectories: the shared-memory data pipe 92 % busy -- the kernel is bound by the operand loads of its four 14 x 14 x 14
+// products (2 x 2 register blocks: 8 64-bit loads per 16 FMAs).  Here the tiles are staged with a leading dimension of 20 (16 rows
+// + 4 pad: a multiple of 4 that keeps the 128-bit accesses of a quarter-warp on distinct banks), so
+// four rows of a column are one aligned 128-bit load, and a lane owns a 4 x 4 block of outputs: 2 128-bit loads per 16 FMAs.
+// Lanes 0..15 do the left product, lanes 16..31 the right one (16 blocks cover a 16 x 16 tile; the pad rows / columns are
+// computed on whatever the pads hold and never stored).  phi_{b+1}^T is not transposed while staging: the right product reads
+// phi_{b+1} as the transposed operand.  Every output is still one FMA per term in ascending k from 0.0f -> same bits.
+namespace schur_detail {
+// o[i][j] = sum_k A(r0 + i, k) * Bop(k, c0 + j);  A column-major with ld LD;  TB = false: B column-major (K x NC, ld LD),
+// TB = true: Bop = B^T with B column-major (NC x K, ld LD)
+constexpr uint32_t LD4 = 20;
+template <uint32_t K, bool TB>
+__device__ __forceinline__ void gemm_4x4_ld(const float *A, const float *B, uint32_t r0, uint32_t c0, float (&o)[4][4])
+{
+#pragma unroll
+    for (uint32_t i = 0; i < 4; ++i)
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) o[i][j] = 0.0f;
+#pragma unroll
+    for (uint32_t kg = 0; kg < (K + 3) / 4; ++kg) {
+        float bq[4][4];                                  // [j][kk] = Bop(4 kg + kk, c0 + j)
+        if constexpr (!TB) {
+#pragma unroll
+            for (uint32_t j = 0; j < 4; ++j) {
+                const float4 f = *reinterpret_cast<const float4 *>(B + (c0 + j) * LD4 + 4 * kg);
+                bq[j][0] = f.x; bq[j][1] = f.y; bq[j][2] = f.z; bq[j][3] = f.w;
+            }
+        }
+#pragma unroll
+        for (uint32_t kk = 0; kk < 4; ++kk) {
+            const uint32_t k = 4 * kg + kk;
+            if (k < K) {
+                const float4 a4 = *reinterpret_cast<const float4 *>(A + k * LD4 + r0);
+                const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+                float bb[4];
+                if constexpr (TB) {
+                    const float4 f = *reinterpret_cast<const float4 *>(B + k * LD4 + c0);
+                    bb[0] = f.x; bb[1] = f.y; bb[2] = f.z; bb[3] = f.w;
+                } else {
+#pragma unroll
+                    for (uint32_t j = 0; j < 4; ++j) bb[j] = bq[j][kk];
+                }
+#pragma unroll
+                for (uint32_t i = 0; i < 4; ++i)
+#pragma unroll
+                    for (uint32_t j = 0; j < 4; ++j) o[i][j] = fma_(a[i], bb[j], o[i][j]);
+            }
+        }
+    }
+}
+}  // namespace schur_detail
+
+template <uint32_t n, uint32_t m>
+__global__ void __launch_bounds__(SchurShape<n, m>::NT)
+schur_phase2_warp_kernel(uint32_t N, float *__restrict__ G, const float *__restrict__ S, float *__restrict__ Pinv)
+{
+    using namespace schur_detail;
+    using K = SchurShape<n, m>;
+    static_assert(n <= 16, "a tile is staged as 16 x 16");
+    constexpr uint32_t nn = K::nn, mm = K::mm, TS = K::P2W_TILE;
+    extern __shared__ __align__(16) float sm[];
+    const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5, b = blockIdx.x * (K::NT / 32) + wib;
+    {
+        const size_t sys = blockIdx.y;
+        G += sys * ((size_t)K::GSET * (N - 1) + nn); S += sys * 3 * (size_t)nn * N; Pinv += sys * 3 * (size_t)nn * N;
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");           // everything phase 1 wrote is visible after this wait
+    if (b >= N) return;
+    float *sTk = sm + wib * (7 * TS), *sTm = sTk + TS, *sTp = sTm + TS, *sPhik = sTp + TS, *sPhiN = sPhik + TS, *sL = sPhiN + TS, *sRr = sL + TS;
+    float *Prow = Pinv + (size_t)b * 3 * nn;
+    const bool has_l = b != 0, has_r = b != N - 1;
+    // With one warp per row there are few warps per SM to hide DRAM latency behind, so every global read of the row is in flight at
+    // once: the five operand tiles go global -> shared memory as 4-byte cp.async copies (no registers, no round trip per loop
+    // iteration), the parked inverses as fully unrolled loads ahead of their stores.
+    auto cp4 = [](float *dst, const float *src) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+    };
+    constexpr uint32_t RN = (nn + 31) / 32, RM = (mm + 31) / 32;
+#pragma unroll
+    for (uint32_t it = 0; it < RN; ++it) {
+        const uint32_t i = lane + 32 * it;
+        if (i < nn) {
+            const uint32_t d = (i / n) * LD4 + i % n;             // column-major, leading dimension LD4
+            cp4(sTk + d, Prow + nn + i);
+            if (has_l) { cp4(sTm + d, Prow - 3 * nn + nn + i); cp4(sPhik + d, S + (size_t)b * 3 * nn + i); }
+            if (has_r) { cp4(sTp + d, Prow + 3 * nn + nn + i); cp4(sPhiN + d, S + (size_t)(b + 1) * 3 * nn + i); }
+        }
+    }
+    // parked inverses -> G (this warp owns the tiles they are parked in; the same lane reads an element here and overwrites it below)
+    {
+        float ql[RN], qr[RM];
+#pragma unroll
+        for (uint32_t it = 0; it < RN; ++it) { const uint32_t i = lane + 32 * it; ql[it] = ((has_l || b == 0) && i < nn) ? Prow[i] : 0.0f; }
+#pragma unroll
+        for (uint32_t it = 0; it < RM; ++it) { const uint32_t i = lane + 32 * it; qr[it] = (has_r && i < mm) ? Prow[2 * nn + i] : 0.0f; }
+        float *Gl = G + (size_t)(has_l ? b - 1 : N - 1) * K::GSET;           // row 0 holds Q_{N-1}^-1 in its pad tile
+#pragma unroll
+        for (uint32_t it = 0; it < RN; ++it) { const uint32_t i = lane + 32 * it; if (i < nn) Gl[i] = ql[it]; }
+#pragma unroll
+        for (uint32_t it = 0; it < RM; ++it) { const uint32_t i = lane + 32 * it; if (has_r && i < mm) G[(size_t)b * K::GSET + nn + i] = qr[it]; }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();
+    const bool rgt = lane >= 16, mine = rgt ? has_r : has_l;
+    const uint32_t r0 = 4 * (lane & 3u), c0 = 4 * ((lane >> 2) & 3u);
+    float o[4][4];
+    if (mine) {
+        // left: theta_k^-1 phi_k ; right: theta_k^-1 phi_{k+1}^T
+        if (rgt) gemm_4x4_ld<n, true>(sTk, sPhiN, r0, c0, o);
+        else gemm_4x4_ld<n, false>(sTk, sPhik, r0, c0, o);
+        float *dst = rgt ? sRr : sL;
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) *reinterpret_cast<float4 *>(dst + (c0 + j) * LD4 + r0) = make_float4(o[0][j], o[1][j], o[2][j], o[3][j]);
+    }
+    __syncwarp();
+    if (mine) {
+        // ... times the neighbour's theta^-1, negated; parked in the (dead) phi buffers for a coalesced write
+        gemm_4x4_ld<n, false>(rgt ? sRr : sL, rgt ? sTp : sTm, r0, c0, o);
+        float *dst = rgt ? sPhiN : sPhik;
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j)
+            *reinterpret_cast<float4 *>(dst + (c0 + j) * LD4 + r0) = make_float4(o[0][j] * -1.0f, o[1][j] * -1.0f, o[2][j] * -1.0f, o[3][j] * -1.0f);
+    }
+    __syncwarp();
+    for (uint32_t i = lane; i < nn; i += 32) {
+        const uint32_t d = (i / n) * LD4 + i % n;
+        if (has_l) Prow[i] = sPhik[d];
+        if (has_r) Prow[2 * nn + i] = sPhiN[d];
     }
 }
 

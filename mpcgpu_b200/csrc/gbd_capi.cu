@@ -639,7 +639,8 @@ int schur_launch(uint32_t N, uint32_t batch, float *G, const float *C, const flo
     using K = gbd::SchurShape<n, m>;
     { const int drc = check_device(); if (drc) return drc; }
     const int team = g_schur_team.load(std::memory_order_relaxed);
-    if (team == 1 || (team < 0 && (uint64_t)batch * N >= 4096u)) {       // batches: one warp per block row, four rows per CTA
+    const bool warp_rows = team == 1 || (team < 0 && (uint64_t)batch * N >= 4096u);
+    if (warp_rows) {                                                      // batches: one warp per block row, four rows per CTA
         constexpr uint32_t RPC = K::NT / 32;
         gbd::schur_phase1_kernel<n, m, true><<<dim3((N + RPC - 1) / RPC, batch), K::NT, RPC * K::P1_STRIDE * sizeof(float), st>>>(
             N, G, C, g, c, S, P, gam, rho);
@@ -649,15 +650,16 @@ int schur_launch(uint32_t N, uint32_t batch, float *G, const float *C, const flo
     {   // phase 2 with programmatic stream serialization: its launch overlaps phase 1, griddepcontrol.wait orders the data
         cudaLaunchConfig_t cfg = {};
         cudaLaunchAttribute at[1];
-        cfg.gridDim = dim3(N, batch);
+        cfg.gridDim = warp_rows ? dim3((N + K::NT / 32 - 1) / (K::NT / 32), batch) : dim3(N, batch);
         cfg.blockDim = dim3(K::NT);
-        cfg.dynamicSmemBytes = K::P2_FLOATS * sizeof(float);
+        cfg.dynamicSmemBytes = (warp_rows ? K::P2W_FLOATS : K::P2_FLOATS) * sizeof(float);
         cfg.stream = st;
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         const float *Sc = S;
-        CK(cudaLaunchKernelEx(&cfg, gbd::schur_phase2_kernel<n, m>, N, G, Sc, P));
+        if (warp_rows) CK(cudaLaunchKernelEx(&cfg, gbd::schur_phase2_warp_kernel<n, m>, N, G, Sc, P));
+        else CK(cudaLaunchKernelEx(&cfg, gbd::schur_phase2_kernel<n, m>, N, G, Sc, P));
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e);
