@@ -39,6 +39,8 @@ namespace schur_detail {
 
 __device__ __forceinline__ float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 
+// (gj_regs: the form the direct solver gbd_bcr.cuh calls with its rows already in registers; the assembly kernels below use the
+// sliding-window form gj_div_window / gj_rcp_warp, which performs the same updates.)
 // Gauss-Jordan on [V | I] (DIM x 2 DIM) by ONE warp with the matrix rows in REGISTERS: lane r < DIM holds row r of the
 // augmented matrix (2 DIM values, the identity half generated in place), the pivot loop is fully unrolled so every
 // register index is static.  Per pivot p the reference updates the DIM+1 columns p .. p+DIM from a snapshot of the
