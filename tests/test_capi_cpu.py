@@ -52,6 +52,15 @@ def test_tuning_knob(capi):
     assert L.gbd_pcg_set_tuning(14, 128, 0, 0, -1) == capi.OK
 
 
+def test_schur_team_knob_returns_the_previous_mode(capi):
+    """gbd_schur_set_team: -1 = by size (default), 0 = CTA per block row, 1 = warp per block row; any negative value means -1."""
+    L = capi.lib()
+    assert L.gbd_schur_set_team(1) == -1
+    assert L.gbd_schur_set_team(0) == 1
+    assert L.gbd_schur_set_team(-7) == 0
+    assert L.gbd_schur_set_team(-1) == -1
+
+
 def test_bad_arguments_are_errors_not_aborts(capi):
     L = capi.lib()
     it, fl = C.c_uint32(), C.c_uint8()
