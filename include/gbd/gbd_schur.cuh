@@ -39,6 +39,19 @@ namespace schur_detail {
 
 __device__ __forceinline__ float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 
+// a / b, IEEE round-to-nearest, bit for bit __fdiv_rn(a, b).  __fdiv_rn leaves its inline sequence (MUFU.RCP + 5 FMAs) for a
+// ~35-instruction subroutine whenever FCHK flags an operand, and an exactly zero numerator is such an operand.  In the
+// Gauss-Jordan steps zero numerators are the rule (the identity half of [V | I], the off-diagonal zeros of a diagonal Q), and one
+// flagged lane sends the whole warp through the subroutine: measured 19 calls per block row, 12 % of the batched kernel's
+// instructions, on the dependent pivot chain.  0 / b for finite non-zero b is the zero whose sign is sign(a) xor sign(b): formed
+// directly, and the division itself runs on a numerator that does not raise the flag.
+__device__ __forceinline__ float div_rn(float a, float b)
+{
+    const bool z = a == 0.0f && b != 0.0f && fabsf(b) < __int_as_float(0x7f800000);
+    const float q = __fdiv_rn(z ? 1.0f : a, b);
+    return z ? __int_as_float((__float_as_int(a) ^ __float_as_int(b)) & (int)0x80000000) : q;
+}
+
 // (gj_regs: the form the direct solver gbd_bcr.cuh calls with its rows already in registers; the assembly kernels below use the
 // sliding-window form gj_div_window / gj_rcp_warp, which performs the same updates.)
 // Gauss-Jordan on [V | I] (DIM x 2 DIM) by ONE warp with the matrix rows in REGISTERS: lane r < DIM holds row r of the
@@ -155,10 +168,10 @@ __device__ __forceinline__ void gj_div_window(float *A, float *snap, uint32_t la
         const float piv = row[0];
         float q, nq;
         if constexpr (TEAM == 16) {
-            q = __fdiv_rn(w[0], piv);
-            nq = __fdiv_rn(row[cI], piv);
+            q = div_rn(w[0], piv);
+            nq = div_rn(row[cI], piv);
         } else {
-            q = nq = __fdiv_rn(upper ? row[cI] : w[0], piv);     // one division sequence serves both kinds of quotient
+            q = nq = div_rn(upper ? row[cI] : w[0], piv);     // one division sequence serves both kinds of quotient
         }
         if (quot && hl <= DIM) nrow[cI] = nq;
         __syncwarp();
